@@ -1,0 +1,192 @@
+/* birdnet_b200 — C ABI of the B200-native batched inference path.
+ *
+ * Drop-in boundary.  The reference (tphakala/rust-birdnet-onnx) has no
+ * FFI of its own (`unsafe_code = "deny"`, Cargo.toml:41); its seam is the set of calls it makes
+ * into the `ort` crate.  Each entry point below names the reference call site it replaces.
+ * Plain C: opaque handles, pointers and sizes only.  Every function returns a bn_status
+ * (0 = ok); the message of the last failure on the calling thread is bn_last_error().
+ *
+ * Threading: a bn_engine may be shared by threads (runs through bn_engine_run serialise on an
+ * internal lock, like the reference's Mutex<Session>, src/classifier.rs:435); a bn_ctx is
+ * single-threaded, one per thread (src/batch_context.rs:56-60).
+ */
+#ifndef BIRDNET_B200_H
+#define BIRDNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes: one per variant of the reference's Error enum (src/error.rs:6-128). */
+typedef enum bn_status {
+    BN_OK = 0,
+    BN_ERR_INPUT_SIZE = 1,             /* Error::InputSize            error.rs:8-14   */
+    BN_ERR_BATCH_INPUT_SIZE = 2,       /* Error::BatchInputSize       error.rs:17-25  */
+    BN_ERR_MODEL_DETECTION = 3,        /* Error::ModelDetection       error.rs:28-32  */
+    BN_ERR_LABEL_COUNT = 4,            /* Error::LabelCount           error.rs:35-41  */
+    BN_ERR_MODEL_PATH_REQUIRED = 5,    /* Error::ModelPathRequired    error.rs:44-45  */
+    BN_ERR_LABELS_REQUIRED = 6,        /* Error::LabelsRequired       error.rs:48-49  */
+    BN_ERR_MODEL_LOAD = 7,             /* Error::ModelLoad            error.rs:52-53  */
+    BN_ERR_LABEL_LOAD = 8,             /* Error::LabelLoad            error.rs:56-62  */
+    BN_ERR_LABEL_PARSE = 9,            /* Error::LabelParse           error.rs:65-66  */
+    BN_ERR_INFERENCE = 10,             /* Error::Inference            error.rs:69-70  */
+    BN_ERR_INVALID_COORDINATES = 11,   /* Error::InvalidCoordinates   error.rs:73-81  */
+    BN_ERR_INVALID_DATE = 12,          /* Error::InvalidDate          error.rs:84-92  */
+    BN_ERR_RANGE_FILTER_INFERENCE = 13,/* Error::RangeFilterInference error.rs:95-96  */
+    BN_ERR_TIMEOUT = 14,               /* Error::Timeout              error.rs:99-103 */
+    BN_ERR_CANCELLED = 15,             /* Error::Cancelled            error.rs:106-107*/
+    BN_ERR_RUNTIME_INIT = 16,          /* Error::RuntimeInit          error.rs:110-111 (no usable CUDA device) */
+    BN_ERR_INVALID_ARGUMENT = 19
+} bn_status;
+
+/* ModelType (src/types.rs:3-11) */
+enum { BN_MODEL_AUTO = -1, BN_MODEL_BIRDNET_V24 = 0, BN_MODEL_BIRDNET_V30 = 1, BN_MODEL_PERCH_V2 = 2 };
+
+typedef struct bn_engine bn_engine;     /* replaces ort::session::Session        */
+typedef struct bn_ctx bn_ctx;           /* replaces ort::io_binding::IoBinding + the host slab */
+typedef struct bn_pool bn_pool;         /* one engine replica + ctx per GPU, host-side gather */
+
+typedef struct bn_device_cfg {
+    int32_t device_id;            /* CUDAConfig::with_device_id, src/cuda_config.rs:179-182 */
+    int32_t model_type_override;  /* BN_MODEL_AUTO or a ModelType (ClassifierBuilder::model_type,
+                                     src/classifier.rs:98-102) */
+    int32_t pack_threads;         /* host threads gathering segments into pinned staging; 0 = auto */
+    int32_t reserved;
+} bn_device_cfg;
+
+#define BN_MAX_DIMS 8
+#define BN_MAX_OUTPUTS 8
+typedef struct bn_tensor_info {
+    char name[64];
+    int32_t rank;
+    int64_t dims[BN_MAX_DIMS];    /* -1 = dynamic, as ort reports it */
+} bn_tensor_info;
+
+/* What session.inputs()/outputs() + detect_model_type give the reference
+ * (src/classifier.rs:353-357, 387-420; src/detection.rs:15-80; src/types.rs:72-85). */
+typedef struct bn_io_info {
+    bn_tensor_info input;
+    int32_t n_outputs;
+    bn_tensor_info outputs[BN_MAX_OUTPUTS];
+    int32_t model_type;
+    uint32_t sample_rate;
+    float segment_duration;
+    uint64_t sample_count;
+    uint64_t num_species;
+    uint64_t embedding_dim;       /* 0 = model has no embeddings (v2.4) */
+} bn_io_info;
+
+/* RunOptions + the monitor thread of Classifier::run_inference (src/classifier.rs:504-574):
+ * the engine polls while it waits for the device.  cancel_flag may be NULL. */
+typedef struct bn_run_opts {
+    const volatile int32_t* cancel_flag;  /* CancellationToken: non-zero = cancelled */
+    int32_t has_timeout;
+    uint64_t timeout_ns;
+} bn_run_opts;
+
+typedef struct bn_pred {
+    uint32_t index;               /* Prediction::index      src/types.rs:95 */
+    float confidence;             /* Prediction::confidence src/types.rs:93 */
+} bn_pred;
+
+/* Borrowed, engine-owned host (pinned) buffers, valid until the next run on the same ctx /
+ * engine — the reference holds the session lock while outputs exist (classifier.rs:628-630). */
+typedef struct bn_outputs {
+    uint64_t batch;
+    uint64_t num_species;
+    const float* logits;          /* [batch][num_species]  PredictionResult::raw_scores */
+    uint64_t embedding_dim;
+    const float* embeddings;      /* [batch][embedding_dim] or NULL */
+    uint64_t topk_stride;         /* slots per segment = min(top_k, num_species) */
+    const uint32_t* topk_count;   /* [batch] predictions that survived min_confidence / range mask */
+    const bn_pred* topk;          /* [batch][topk_stride], first topk_count[i] valid, sorted */
+} bn_outputs;
+
+/* ---- errors ---------------------------------------------------------------------- */
+const char* bn_last_error(void);                 /* payload text ({0} / {reason}) of the last failure */
+void bn_last_error_detail(uint64_t out[3]);      /* BatchInputSize: {index, expected, got}; InputSize: {0, expected, got} */
+const char* bn_version(void);
+
+/* ---- load time --------------------------------------------------------------------
+ * bn_engine_create  <- Session::builder().with_execution_providers(..).commit_from_file(path)
+ *                      src/classifier.rs:340-350 (+ detect_model_type, classifier.rs:357)
+ * bn_engine_io_info <- session.inputs()/outputs() shapes, src/classifier.rs:387-420
+ * bn_model_inspect  :  same parse + detection with no GPU touched (load-time checks, tests) */
+int bn_engine_create(const char* onnx_path, const bn_device_cfg* cfg, bn_engine** out);
+void bn_engine_destroy(bn_engine* engine);
+int bn_engine_io_info(const bn_engine* engine, bn_io_info* out);
+int bn_model_inspect(const char* onnx_path, int32_t model_type_override, bn_io_info* out);
+/* detect_model_type on explicit shapes (src/detection.rs:15-80); shapes are rank-prefixed rows */
+int bn_detect_model_type(const int64_t* input_dims, int32_t input_rank, const int64_t* output_dims,
+                         const int32_t* output_ranks, int32_t n_outputs, int32_t model_type_override,
+                         bn_io_info* out);
+
+/* ---- fused epilogue configuration ---------------------------------------------------
+ * top_k / min_confidence <- ClassifierBuilder::top_k / min_confidence (classifier.rs:118-129)
+ *                           consumed by top_k_predictions (src/postprocess.rs:40-87)
+ * range filter           <- filter_predictions_impl (src/rangefilter.rs:333-386) as a dense
+ *                           per-class tri-state: 0 absent (keep), 1 keep (x score if rerank), 2 drop */
+int bn_engine_set_postprocess(bn_engine* engine, uint64_t top_k, int32_t has_min_confidence, float min_confidence);
+int bn_engine_set_range_filter(bn_engine* engine, const uint8_t* state, const float* score, uint64_t n, int32_t rerank);
+int bn_engine_clear_range_filter(bn_engine* engine);
+
+/* ---- hot path ----------------------------------------------------------------------
+ * bn_engine_run <- Value::from_array + session.run_with_options (classifier.rs:698-723)
+ *                  validation order of predict_batch (classifier.rs:681-696)
+ * bn_ctx_create <- BatchInferenceContext::new / session.create_binding (batch_context.rs:102-133)
+ * bn_ctx_run    <- prepare_input + bind_outputs_to_device + run_binding_with_options +
+ *                  synchronize + extract_outputs (batch_context.rs:188-338, classifier.rs:839-865)
+ * seg_lens[i] is the sample count of segment i (slices carry their length in Rust). */
+int bn_engine_run(bn_engine* engine, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
+                  const bn_run_opts* opts, bn_outputs* out);
+int bn_ctx_create(bn_engine* engine, uint64_t max_batch_size, bn_ctx** out);
+void bn_ctx_destroy(bn_ctx* ctx);
+int bn_ctx_run(bn_ctx* ctx, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
+               const bn_run_opts* opts, bn_outputs* out);
+uint64_t bn_ctx_max_batch_size(const bn_ctx* ctx);     /* batch_context.rs:137-140 */
+uint64_t bn_ctx_input_buffer_bytes(const bn_ctx* ctx); /* batch_context.rs:155-158 */
+/* Device-resident variant: `d_audio` is a [batch][sample_count] FP32 device buffer on the engine's
+ * GPU (bench: inputs already in HBM).  fetch_outputs != 0 copies results to the pinned host slab. */
+int bn_ctx_run_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs,
+                      const bn_run_opts* opts, bn_outputs* out);
+/* Intermediate tensors of the last run, by ONNX value name ("spec", ...) — parity tests. */
+int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_elems, uint64_t* elems_out);
+int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems);
+/* Kernel launches enqueued by the last run on this ctx, and per-stage device times (ms) of the
+ * last run when profiling was enabled with bn_ctx_set_profiling(ctx, 1). */
+uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx);
+int bn_ctx_set_profiling(bn_ctx* ctx, int32_t enabled);
+int bn_ctx_stage_times(const bn_ctx* ctx, float* ms_out, char (*names_out)[48], uint64_t cap, uint64_t* n_out);
+void* bn_ctx_stream(bn_ctx* ctx);                      /* cudaStream_t the kernels run on */
+
+/* RangeFilter::filter_predictions / filter_batch_predictions on lists already selected
+ * (src/rangefilter.rs:527-579), executed on the engine's device. */
+int bn_range_filter_apply(bn_engine* engine, const bn_pred* in, const uint32_t* in_count, uint64_t rows,
+                          uint64_t stride, const uint8_t* state, const float* score, uint64_t n, int32_t rerank,
+                          bn_pred* out, uint32_t* out_count);
+/* top_k_predictions on caller-supplied logits (src/postprocess.rs:40-87) through the same
+ * epilogue kernel: known-answer tests of the reference run against this. */
+int bn_topk_apply(bn_engine* engine, const float* logits, uint64_t rows, uint64_t n, uint64_t top_k,
+                  int32_t has_min_confidence, float min_confidence, const uint8_t* state, const float* score,
+                  int32_t rerank, bn_pred* out, uint32_t* out_count);
+
+/* ---- multi-GPU: contiguous block partition, no collective ------ */
+int bn_pool_create(const char* onnx_path, const int32_t* device_ids, int32_t n_devices, int32_t model_type_override,
+                   uint64_t ctx_batch, bn_pool** out);
+void bn_pool_destroy(bn_pool* pool);
+int bn_pool_set_postprocess(bn_pool* pool, uint64_t top_k, int32_t has_min_confidence, float min_confidence);
+int bn_pool_set_range_filter(bn_pool* pool, const uint8_t* state, const float* score, uint64_t n, int32_t rerank);
+/* Runs all segments; results are gathered in caller order into caller-provided host arrays:
+ * logits [n_segments][num_species], embeddings (or NULL), topk [n_segments][topk_stride]. */
+int bn_pool_run(bn_pool* pool, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t n_segments,
+                const bn_run_opts* opts, float* logits, float* embeddings, bn_pred* topk, uint32_t* topk_count,
+                uint64_t topk_stride);
+int bn_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIRDNET_B200_H */

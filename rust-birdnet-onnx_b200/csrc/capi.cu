@@ -1,0 +1,280 @@
+// extern "C" surface declared in include/birdnet_b200.h.
+#include <algorithm>
+#include <cstring>
+
+#include "engine.h"
+
+using namespace bn;
+
+extern "C" {
+
+const char* bn_last_error(void) { return last_error().c_str(); }
+void bn_last_error_detail(uint64_t out[3]) {
+    const uint64_t* d = last_detail();
+    out[0] = d[0]; out[1] = d[1]; out[2] = d[2];
+}
+const char* bn_version(void) { return "birdnet_b200 0.1.0 (sm_100a)"; }
+
+int bn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bn_engine_create(const char* onnx_path, const bn_device_cfg* cfg, bn_engine** out) {
+    return engine_create(onnx_path, cfg, out);
+}
+void bn_engine_destroy(bn_engine* engine) { delete engine; }
+
+int bn_engine_io_info(const bn_engine* engine, bn_io_info* out) {
+    if (!engine || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    *out = engine->info;
+    return BN_OK;
+}
+
+int bn_model_inspect(const char* onnx_path, int32_t model_type_override, bn_io_info* out) {
+    if (!out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    Plan plan;
+    int st = load_plan(onnx_path, model_type_override, plan);
+    if (st != BN_OK) return st;
+    return fill_io_info(plan, out);
+}
+
+int bn_detect_model_type(const int64_t* input_dims, int32_t input_rank, const int64_t* output_dims,
+                         const int32_t* output_ranks, int32_t n_outputs, int32_t model_type_override,
+                         bn_io_info* out) {
+    if (!out || (input_rank > 0 && !input_dims)) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<int64_t> in(input_dims, input_dims + std::max(0, input_rank));
+    std::vector<std::vector<int64_t>> outs;
+    const int64_t* p = output_dims;
+    for (int i = 0; i < n_outputs; ++i) {
+        outs.emplace_back(p, p + output_ranks[i]);
+        p += output_ranks[i];
+    }
+    int mt = -1, sc = 0, ns = 0, ed = 0;
+    std::string reason;
+    if (!detect_model_type(in, outs, model_type_override, &mt, &sc, &ns, &ed, &reason))
+        return set_error(BN_ERR_MODEL_DETECTION, reason);
+    memset(out, 0, sizeof(*out));
+    out->model_type = mt;
+    out->sample_rate = mt == MT_BIRDNET_V24 ? 48000u : 32000u;
+    out->segment_duration = mt == MT_BIRDNET_V24 ? 3.0f : 5.0f;
+    out->sample_count = (uint64_t)sc;
+    out->num_species = (uint64_t)ns;
+    out->embedding_dim = (uint64_t)ed;
+    out->n_outputs = n_outputs;
+    return BN_OK;
+}
+
+int bn_engine_set_postprocess(bn_engine* engine, uint64_t top_k, int32_t has_min_confidence, float min_confidence) {
+    if (!engine) return set_error(BN_ERR_INVALID_ARGUMENT, "null engine");
+    std::lock_guard<std::mutex> lk(engine->post_mu);
+    engine->post.top_k = top_k;
+    engine->post.has_min_conf = has_min_confidence ? 1 : 0;
+    engine->post.min_conf = min_confidence;
+    return BN_OK;
+}
+
+static int make_range(int device, const uint8_t* state, const float* score, uint64_t n, int rerank,
+                      std::shared_ptr<RangeDev>& out) {
+    if (!state || !score || n == 0) return set_error(BN_ERR_INVALID_ARGUMENT, "range filter needs state and score arrays");
+    for (uint64_t i = 0; i < n; ++i)
+        if (state[i] > 2) return set_error(BN_ERR_INVALID_ARGUMENT, "range state must be 0, 1 or 2");
+    BN_CUDA(cudaSetDevice(device));
+    auto r = std::make_shared<RangeDev>();
+    r->device = device;
+    r->n = n;
+    r->rerank = rerank ? 1 : 0;
+    BN_CUDA(cudaMalloc(&r->state, n));
+    BN_CUDA(cudaMalloc(&r->score, n * sizeof(float)));
+    BN_CUDA(cudaMemcpy(r->state, state, n, cudaMemcpyHostToDevice));
+    BN_CUDA(cudaMemcpy(r->score, score, n * sizeof(float), cudaMemcpyHostToDevice));
+    out = r;
+    return BN_OK;
+}
+
+int bn_engine_set_range_filter(bn_engine* engine, const uint8_t* state, const float* score, uint64_t n, int32_t rerank) {
+    if (!engine) return set_error(BN_ERR_INVALID_ARGUMENT, "null engine");
+    if (n != engine->info.num_species)
+        return set_error(BN_ERR_INVALID_ARGUMENT, "range filter length " + std::to_string(n) + " != num_species " + std::to_string(engine->info.num_species));
+    std::shared_ptr<RangeDev> r;
+    int st = make_range(engine->device, state, score, n, rerank, r);
+    if (st != BN_OK) return st;
+    std::lock_guard<std::mutex> lk(engine->post_mu);
+    engine->post.range = r;
+    return BN_OK;
+}
+
+int bn_engine_clear_range_filter(bn_engine* engine) {
+    if (!engine) return set_error(BN_ERR_INVALID_ARGUMENT, "null engine");
+    std::lock_guard<std::mutex> lk(engine->post_mu);
+    engine->post.range.reset();
+    return BN_OK;
+}
+
+// one context per calling thread, grown on demand (predict_batch allocates per call in the
+// reference: classifier.rs:701-710)
+static int thread_ctx_for(bn_engine* e, uint64_t batch, bn_ctx** out) {
+    std::lock_guard<std::mutex> lk(e->ctx_mu);
+    auto id = std::this_thread::get_id();
+    auto it = e->thread_ctx.find(id);
+    if (it != e->thread_ctx.end() && it->second->max_batch >= batch) { *out = it->second; return BN_OK; }
+    uint64_t cap = 1;
+    while (cap < batch) cap <<= 1;
+    if (it != e->thread_ctx.end()) { delete it->second; e->thread_ctx.erase(it); }
+    bn_ctx* c = nullptr;
+    int st = ctx_create(e, cap, &c);
+    if (st != BN_OK) return st;
+    e->thread_ctx[id] = c;
+    *out = c;
+    return BN_OK;
+}
+
+int bn_engine_run(bn_engine* engine, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
+                  const bn_run_opts* opts, bn_outputs* out) {
+    if (!engine || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (batch == 0) { memset(out, 0, sizeof(*out)); return BN_OK; }
+    if (!seg_ptrs || !seg_lens) return set_error(BN_ERR_INVALID_ARGUMENT, "null segment array");
+    // validate before any allocation (classifier.rs:688-696)
+    const uint64_t S = engine->info.sample_count;
+    for (uint64_t i = 0; i < batch; ++i)
+        if (seg_lens[i] != S) return set_error_detail(BN_ERR_BATCH_INPUT_SIZE, "batch input size mismatch", i, S, seg_lens[i]);
+    bn_ctx* c = nullptr;
+    int st = thread_ctx_for(engine, batch, &c);
+    if (st != BN_OK) return st;
+    return ctx_run_host(c, seg_ptrs, seg_lens, batch, false, opts, out);
+}
+
+int bn_ctx_create(bn_engine* engine, uint64_t max_batch_size, bn_ctx** out) {
+    if (!engine || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (engine->info.model_type == BN_MODEL_PERCH_V2)      // batch_context.rs:107-114
+        return set_error(BN_ERR_INFERENCE, "BatchInferenceContext does not yet support PerchV2 models. Use predict_batch() instead.");
+    return ctx_create(engine, max_batch_size, out);
+}
+void bn_ctx_destroy(bn_ctx* ctx) { delete ctx; }
+
+int bn_ctx_run(bn_ctx* ctx, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
+               const bn_run_opts* opts, bn_outputs* out) {
+    return ctx_run_host(ctx, seg_ptrs, seg_lens, batch, true, opts, out);
+}
+uint64_t bn_ctx_max_batch_size(const bn_ctx* ctx) { return ctx ? ctx->max_batch : 0; }
+uint64_t bn_ctx_input_buffer_bytes(const bn_ctx* ctx) {
+    return ctx ? ctx->max_batch * (uint64_t)ctx->eng->plan.sample_count * sizeof(float) : 0;
+}
+
+int bn_ctx_run_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs,
+                      const bn_run_opts* opts, bn_outputs* out) {
+    if (!d_audio && batch) return set_error(BN_ERR_INVALID_ARGUMENT, "null device buffer");
+    return ctx_run_device(ctx, d_audio, batch, fetch_outputs != 0, opts, out);
+}
+
+int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_elems, uint64_t* elems_out) {
+    if (!ctx || !name) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    const Plan& p = ctx->eng->plan;
+    for (size_t i = 0; i < p.tensors.size(); ++i) {
+        if (p.tensors[i].name != name) continue;
+        if (p.tensors[i].scale_base >= 0) return set_error(BN_ERR_INVALID_ARGUMENT, "tensor is virtual (gated)");
+        uint64_t per = p.tensors[i].elems();
+        if (elems_out) *elems_out = per;
+        if (!dst) return BN_OK;
+        uint64_t n = std::min<uint64_t>(dst_elems, per * ctx->max_batch);
+        BN_CUDA(cudaSetDevice(ctx->eng->device));
+        BN_CUDA(cudaStreamSynchronize(ctx->stream));
+        BN_CUDA(cudaMemcpy(dst, ctx->d_tensor[i], n * sizeof(float), cudaMemcpyDeviceToHost));
+        return BN_OK;
+    }
+    return set_error(BN_ERR_INVALID_ARGUMENT, std::string("no tensor named '") + name + "'");
+}
+
+int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems) {
+    if (!ctx || !dst) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (!ctx->d_norm) return set_error(BN_ERR_INVALID_ARGUMENT, "model has no normaliser");
+    uint64_t n = std::min<uint64_t>(dst_elems, ctx->max_batch * (uint64_t)ctx->eng->plan.sample_count);
+    BN_CUDA(cudaSetDevice(ctx->eng->device));
+    BN_CUDA(cudaStreamSynchronize(ctx->stream));
+    BN_CUDA(cudaMemcpy(dst, ctx->d_norm, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return BN_OK;
+}
+
+uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+int bn_ctx_set_profiling(bn_ctx* ctx, int32_t enabled) {
+    if (!ctx) return set_error(BN_ERR_INVALID_ARGUMENT, "null ctx");
+    ctx->profiling = enabled != 0;
+    return BN_OK;
+}
+int bn_ctx_stage_times(const bn_ctx* ctx, float* ms_out, char (*names_out)[48], uint64_t cap, uint64_t* n_out) {
+    if (!ctx || !n_out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    uint64_t n = ctx->prof_ms.size();
+    *n_out = n;
+    for (uint64_t i = 0; i < std::min(n, cap); ++i) {
+        if (ms_out) ms_out[i] = ctx->prof_ms[i];
+        if (names_out) { memset(names_out[i], 0, 48); strncpy(names_out[i], ctx->prof_names[i].c_str(), 47); }
+    }
+    return BN_OK;
+}
+void* bn_ctx_stream(bn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int bn_range_filter_apply(bn_engine* engine, const bn_pred* in, const uint32_t* in_count, uint64_t rows,
+                          uint64_t stride, const uint8_t* state, const float* score, uint64_t n, int32_t rerank,
+                          bn_pred* out, uint32_t* out_count) {
+    if (!out || !out_count) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    const int device = engine ? engine->device : 0;      // NULL engine: device 0
+    if (rows == 0) return BN_OK;
+    if (stride == 0) { memset(out_count, 0, rows * sizeof(uint32_t)); return BN_OK; }
+    if (!in || !in_count) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    BN_CUDA(cudaSetDevice(device));
+    BN_CUDA(init_kernels_for_device());
+    std::shared_ptr<RangeDev> r;
+    if (state) { int st = make_range(device, state, score, n, rerank, r); if (st != BN_OK) return st; }
+    Pred *d_in = nullptr, *d_out = nullptr;
+    uint32_t *d_ic = nullptr, *d_oc = nullptr;
+    size_t bytes = rows * stride * sizeof(Pred);
+    BN_CUDA(cudaMalloc(&d_in, bytes));
+    BN_CUDA(cudaMalloc(&d_out, bytes));
+    BN_CUDA(cudaMalloc(&d_ic, rows * sizeof(uint32_t)));
+    BN_CUDA(cudaMalloc(&d_oc, rows * sizeof(uint32_t)));
+    cudaError_t ce = cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d_ic, in_count, rows * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = launch_range_filter((const Pred*)d_in, d_ic, (int)rows, (int)stride, r ? r->state : nullptr, r ? r->score : nullptr,
+                                                    (int)n, rerank ? 1 : 0, d_out, d_oc, 0);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out_count, d_oc, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ic); cudaFree(d_oc);
+    if (ce != cudaSuccess) return cuda_fail(ce, "bn_range_filter_apply");
+    return BN_OK;
+}
+
+int bn_topk_apply(bn_engine* engine, const float* logits, uint64_t rows, uint64_t n, uint64_t top_k,
+                  int32_t has_min_confidence, float min_confidence, const uint8_t* state, const float* score,
+                  int32_t rerank, bn_pred* out, uint32_t* out_count) {
+    if (!out_count) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    const int device = engine ? engine->device : 0;      // NULL engine: device 0
+    if (rows == 0) return BN_OK;
+    uint64_t k = std::min(top_k, n);                      // postprocess.rs:46-50
+    if (k == 0 || n == 0) { memset(out_count, 0, rows * sizeof(uint32_t)); return BN_OK; }
+    if (!logits || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    BN_CUDA(cudaSetDevice(device));
+    BN_CUDA(init_kernels_for_device());
+    std::shared_ptr<RangeDev> r;
+    if (state) { int st = make_range(device, state, score, n, rerank, r); if (st != BN_OK) return st; }
+    float* d_l = nullptr;
+    Pred* d_out = nullptr;
+    uint32_t* d_oc = nullptr;
+    BN_CUDA(cudaMalloc(&d_l, rows * n * sizeof(float)));
+    BN_CUDA(cudaMalloc(&d_out, rows * k * sizeof(Pred)));
+    BN_CUDA(cudaMalloc(&d_oc, rows * sizeof(uint32_t)));
+    cudaError_t ce = cudaMemcpy(d_l, logits, rows * n * sizeof(float), cudaMemcpyHostToDevice);
+    TopkParams tp{};
+    tp.logits = d_l; tp.batch = (int)rows; tp.n = (int)n; tp.k = (uint32_t)k;
+    tp.has_min_conf = has_min_confidence ? 1 : 0; tp.min_conf = min_confidence;
+    tp.range_state = r ? r->state : nullptr; tp.range_score = r ? r->score : nullptr; tp.rerank = rerank ? 1 : 0;
+    tp.out = d_out; tp.out_count = d_oc;
+    if (ce == cudaSuccess) ce = launch_topk(tp, 0);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, rows * k * sizeof(Pred), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out_count, d_oc, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_l); cudaFree(d_out); cudaFree(d_oc);
+    if (ce != cudaSuccess) return cuda_fail(ce, "bn_topk_apply");
+    return BN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Engine internals shared by engine.cu / capi.cu / pool.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/birdnet_b200.h"
+#include "kernels.h"
+#include "plan.h"
+
+namespace bn {
+
+// ---- thread-local error channel ------------------------------------------------------
+int set_error(int status, const std::string& msg);
+int set_error_detail(int status, const std::string& msg, uint64_t a, uint64_t b, uint64_t c);
+int cuda_fail(cudaError_t e, const char* what);   // -> BN_ERR_INFERENCE / BN_ERR_RUNTIME_INIT
+const std::string& last_error();
+const uint64_t* last_detail();
+int load_plan(const char* path, int override_type, Plan& plan);
+
+#define BN_CUDA(expr)                                                     \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) return ::bn::cuda_fail(_e, #expr);         \
+    } while (0)
+
+struct DevOp {
+    float* weight = nullptr;
+    float* bias = nullptr;
+};
+
+struct RangeDev {   // dense per-class tri-state on the device
+    uint8_t* state = nullptr;
+    float* score = nullptr;
+    uint64_t n = 0;
+    int rerank = 0;
+    int device = 0;
+    ~RangeDev();
+};
+
+struct PostCfg {
+    uint64_t top_k = 10;          // ClassifierBuilder default, src/classifier.rs:72
+    int has_min_conf = 0;         // min_confidence: None,      src/classifier.rs:73
+    float min_conf = 0.f;
+    std::shared_ptr<RangeDev> range;
+};
+
+}  // namespace bn
+
+struct bn_engine {
+    int device = 0;
+    int pack_threads = 0;
+    bn::Plan plan;
+    bn_io_info info{};
+    std::vector<bn::DevOp> dev_ops;
+    std::vector<float*> d_basis;   // per front-end branch [n_fft][ldb]
+    std::vector<int> ldb;
+    std::mutex post_mu;
+    bn::PostCfg post;
+    std::mutex ctx_mu;
+    std::map<std::thread::id, bn_ctx*> thread_ctx;   // bn_engine_run: one context per calling thread
+    ~bn_engine();
+};
+
+struct bn_ctx {
+    bn_engine* eng = nullptr;
+    uint64_t max_batch = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t done = nullptr;
+    float* h_in = nullptr;       // pinned [max_batch][S]
+    float* d_in = nullptr;       // [max_batch][S]
+    float* d_norm = nullptr;     // [max_batch][S] normalised audio (v2.4 front-end)
+    std::vector<float*> d_tensor;   // per plan tensor (aliases resolved to their root)
+    float* h_logits = nullptr;   // pinned
+    float* h_emb = nullptr;      // pinned
+    bn::Pred* d_topk = nullptr;
+    uint32_t* d_count = nullptr;
+    bn::Pred* h_topk = nullptr;
+    uint32_t* h_count = nullptr;
+    uint64_t topk_cap = 0;       // slots per segment currently allocated
+    std::shared_ptr<bn::RangeDev> range_in_flight;
+    bool draining = false;
+    uint64_t last_launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<std::string> prof_names;
+    std::vector<float> prof_ms;
+    std::vector<std::thread> packers;
+    ~bn_ctx();
+};
+
+namespace bn {
+int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out);
+int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out);
+int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
+                 bool check_max_first, const bn_run_opts* opts, bn_outputs* out);
+int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts,
+                   bn_outputs* out);
+int fill_io_info(const Plan& plan, bn_io_info* out);
+}  // namespace bn

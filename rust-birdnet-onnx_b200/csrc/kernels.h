@@ -1,0 +1,73 @@
+// Launchers for the sm_100a kernels of the hot path.  All tensors are NHWC FP32 in HBM.
+// Every launcher enqueues on `stream` and returns the cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace bn {
+
+enum { KACT_NONE = 0, KACT_SILU = 1, KACT_SIGMOID = 2 };   // == plan.h Act
+
+// must be called once per device before launch_topk / launch_range_filter (opt-in smem size)
+cudaError_t init_kernels_for_device();
+
+// C-ABI mirror (include/birdnet_b200.h: bn_pred)
+struct Pred { uint32_t index; float confidence; };
+
+// ---- front-end (row A7) -----------------------------------------------------------
+// per-segment min/max normalise: y = ((x - min) / (max(x - min) + eps) - half) * two
+cudaError_t launch_minmax_normalize(const float* x, float* y, int batch, int sample_count,
+                                    float eps, float half, float two, cudaStream_t stream);
+
+// framed DFT(real) x mel (pre-multiplied basis [n_fft][ldb]) -> square -> pow(exponent);
+// writes channel `ch` of the NHWC spectrogram [B][n_mels][n_frames][n_ch]
+cudaError_t launch_spectrogram_v24(const float* xnorm, const float* basis, int ldb, float* spec,
+                                   int batch, int sample_count, int n_fft, int hop, int n_frames,
+                                   int n_mels, int n_ch, int ch, float exponent, cudaStream_t stream);
+
+// ---- CNN (row A8) -----------------------------------------------------------------
+struct ConvParams {
+    const float* in;        // [B][hin][win][cin]
+    const float* in_scale;  // [B][cin] squeeze-excite gate or nullptr
+    const float* weight;    // [k*k*cin][ldw]
+    const float* bias;      // [cout]
+    const float* residual;  // [B][hout][wout][cout] or nullptr (added after the activation)
+    float* out;             // [B][hout][wout][cout]
+    int batch, hin, win, cin, hout, wout, cout, ldw, k, stride, pad, act;
+};
+cudaError_t launch_conv_igemm(const ConvParams& p, cudaStream_t stream);
+
+struct DwParams {
+    const float* in;      // [B][hin][win][c]
+    const float* weight;  // [k*k][c]
+    const float* bias;    // [c]
+    float* out;           // [B][hout][wout][c]
+    int batch, hin, win, c, hout, wout, k, stride, pad, act;
+};
+cudaError_t launch_dwconv(const DwParams& p, cudaStream_t stream);
+
+// global average pool: [B][hw][c] -> [B][c]
+cudaError_t launch_gap(const float* in, float* out, int batch, int hw, int c, cudaStream_t stream);
+
+// ---- epilogue (rows A4 / A6) ------------------------------------------------------
+struct TopkParams {
+    const float* logits;        // [B][n]
+    int batch, n;
+    uint32_t k;                 // already clamped to n by the caller; 0 => counts are all 0
+    int has_min_conf;
+    float min_conf;
+    const uint8_t* range_state; // [n] 0 = absent (keep), 1 = keep * score, 2 = drop; or nullptr
+    const float* range_score;   // [n]
+    int rerank;
+    Pred* out;                  // [B][k]
+    uint32_t* out_count;        // [B]
+};
+cudaError_t launch_topk(const TopkParams& p, cudaStream_t stream);
+
+// range filter applied to already-selected predictions (RangeFilter::filter_predictions,
+// src/rangefilter.rs:333-386): in/out lists of `stride` slots per row, counts per row.
+cudaError_t launch_range_filter(const Pred* in, const uint32_t* in_count, int rows, int stride,
+                                const uint8_t* state, const float* score, int n, int rerank,
+                                Pred* out, uint32_t* out_count, cudaStream_t stream);
+
+}  // namespace bn
