@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: BirdNET v2.4 segments/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (CUDA engine)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the
+                                                             # reference's path on the host cores
+
+A step = one pass of the whole hot path over one batch of 256 synthetic 48 kHz segments
+(BASELINE.json configs[1]: create_batch_context(256) + predict_batch_with_context).
+
+  value : device-timed throughput with the batch already resident in HBM (front-end + CNN + fused
+          top-k epilogue + D2H of the results), K steps enqueued back to back, CUDA events on the
+          engine's own stream, max over ranks.
+  e2e   : the same metric through the public API (Classifier.predict_batch_with_context) with
+          HOST segment slices: host gather into pinned staging, H2D, kernels, D2H and the
+          host-side Prediction objects are all inside the timed region.
+  roofline : the dominant kernel of the step, timed live with CUDA events (profiling mode of the
+          engine) against MEASURED_PEAKS.json.
+  cpu_baseline : oracle port (torch CPU FP32 stand-in for ORT CPU) on a
+          bounded sample, rank 0 at N=1 only.
+
+Multi-GPU: one process per GPU (torchrun); segments shard across ranks with no data-path
+collective; NCCL is used only for the barrier and the max-over-ranks time (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "rust-birdnet-onnx_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "birdnet_v2.4_segments_per_sec"
+UNIT = "segments/s"
+BATCH = 256
+FAMILY = "birdnet_v24"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on the host cores
+# ----------------------------------------------------------------------------------------------
+def _cpu_oracle_rate(n_target_s: float, batch: int, max_segments: int):
+    import torch
+    from birdnet_b200.modelgen import get_spec, synth
+    from birdnet_b200.modelgen.make_models import ensure_model
+    from oracle.model_oracle import ModelOracle, load_initializers
+    from oracle import postprocess_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = get_spec(FAMILY)
+    orc = ModelOracle(spec, load_initializers(ensure_model(FAMILY)))
+    audio = synth.batch(0, batch, 144000, 48000)
+
+    def step():
+        logits, _ = orc.logits_and_embeddings(audio)
+        po.top_k_batch(logits, 5, 0.1)
+    step()                                   # warm-up (thread pools, FFT plans)
+    t0 = time.perf_counter()
+    step()
+    one = time.perf_counter() - t0
+    n_steps = int(max(1, min(max_segments // batch, n_target_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        step()
+    dt = time.perf_counter() - t0
+    return (n_steps * batch) / dt, cores, n_steps * batch, dt, step
+
+
+def run_reference(args):
+    rank, local, world = _dist()
+    if rank != 0:
+        return 0
+    batch = 32                               # BASELINE.json configs[0]: predict_batch batch=32 on CPU
+    rate, cores, nseg, dt, step = _cpu_oracle_rate(4.0, batch, 64)   # builds the oracle + a short calibration
+    for _ in range(max(args.warmup, 0)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * batch / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BirdNET v2.4-like (random-init seed 0) batch=256 hot path; this arm: "
+                               "bounded sample, batch 32 per step on the host cores",
+                   "global_batch": batch, "top_k": 5, "min_confidence": 0.1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {batch} segments, torch {__import__('torch').__version__} CPU FP32 "
+                                   "oracle port (ORT CPU cannot run in this image)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# this build
+# ----------------------------------------------------------------------------------------------
+def _stage_roofline(spec, stage_times, batch, peaks):
+    """Per-stage algorithmic work -> achieved rate; returns (dominant stage dict, all stages)."""
+    rows = {r["name"]: r for r in spec.layer_table()}
+    fe = spec.frontend
+    out = []
+    total = sum(ms for _, ms in stage_times) or 1.0
+    for name, ms in stage_times:
+        if ms <= 0:
+            continue
+        base = name[:-5] if name.endswith(".conv") else name
+        if "_" in base and base.rsplit("_", 1)[1].isdigit() and base.rsplit("_", 1)[0] in rows:
+            base = base.rsplit("_", 1)[0]
+        d = {"stage": name, "ms": ms, "share": ms / total}
+        if base in rows and rows[base]["kind"] in ("conv", "gemm"):
+            r = rows[base]
+            flops = 2.0 * r["macs"] * batch
+            d.update(bound="tensor", achieved=flops / (ms * 1e-3) / 1e12, peak=peaks["tf_sust"], unit="TFLOP/s",
+                     alg_per_segment=2 * r["macs"])
+        elif base in rows:                                      # depthwise: bandwidth-bound
+            r = rows[base]
+            byts = 4.0 * (r["in_elems"] + r["out_elems"] + r["w_elems"] / batch) * batch
+            d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                     alg_per_segment=4 * (r["in_elems"] + r["out_elems"]))
+        elif name.startswith("spectrogram"):
+            s = fe.specs[int(name[-1])]
+            t = s.n_frames(fe.sample_count)
+            # algorithmic bytes: audio read once (shared by both branches: counted half each) + spectrogram written once
+            byts = (fe.sample_count * 4 / len(fe.specs) + s.n_mels * t * 4) * batch
+            d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                     alg_per_segment=fe.sample_count * 4 / len(fe.specs) + s.n_mels * t * 4,
+                     tensor_equiv_tflops=2.0 * t * s.n_fft * s.n_mels * batch / (ms * 1e-3) / 1e12)
+        elif name == "normalize":
+            byts = fe.sample_count * 4 * 2 * batch
+            d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                     alg_per_segment=fe.sample_count * 8)
+        elif name == "topk_epilogue":
+            byts = (spec.num_species * 4 + 5 * 8) * batch
+            d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                     alg_per_segment=spec.num_species * 4 + 40)
+        else:
+            continue
+        d["frac"] = d["achieved"] / d["peak"]
+        out.append(d)
+    dom = max(out, key=lambda x: x["ms"]) if out else None
+    return dom, out
+
+
+def run_ours(args):
+    import torch
+    import birdnet_b200 as bb
+    from birdnet_b200.modelgen import get_spec, synth
+    from birdnet_b200.modelgen.make_models import ensure_model, synthetic_labels
+
+    rank, local, world = _dist()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = _peaks()
+    spec = get_spec(FAMILY)
+    path = ensure_model(FAMILY)
+    clf = (bb.Classifier.builder().model_path(path).labels(synthetic_labels(spec.num_species))
+           .top_k(5).min_confidence(0.1).device_id(local).build())
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    # each rank owns its own shard of the synthetic stream (weak scaling: 256 segments per rank per step)
+    audio = synth.batch(rank * B, B, 144000, 48000)
+    segs = list(audio)
+    ctx = clf.create_batch_context(B)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident input, K steps back to back on the engine's stream ------------
+    d_audio = torch.from_numpy(audio).cuda(local)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+    for _ in range(W):
+        ctx.enqueue_device(d_audio.data_ptr(), B, True)
+    ctx.wait()
+    launches_per_step = ctx.last_launch_count()
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(K):
+        ctx.enqueue_device(d_audio.data_ptr(), B, True)
+    ev1.record(stream)
+    ctx.wait()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    # keep the GPU busy a little longer so the 100 ms sampler sees load even for short runs
+    t_end = time.perf_counter() + 0.6
+    while time.perf_counter() < t_end:
+        ctx.enqueue_device(d_audio.data_ptr(), B, False)
+        ctx.wait()
+    clocks = sampler.stop()
+    if dist is not None:
+        t = torch.tensor([dev_ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = world * B * K / (dev_ms * 1e-3)
+
+    # ---- e2e: public API with host slices, `depth` contexts driven by `depth` host threads ------
+    depth = max(1, args.pipeline_depth)
+    ctxs = [ctx] + [clf.create_batch_context(B) for _ in range(depth - 1)]
+    for c in ctxs:
+        for _ in range(2):
+            clf.predict_batch_with_context(c, segs)
+    n_e2e = K
+    sink = [0] * depth
+
+    def e2e_worker(t):
+        for i in range(t, n_e2e, depth):
+            res = clf.predict_batch_with_context(ctxs[t], segs)
+            sink[t] += len(res[0].predictions) + len(res)
+    barrier()
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(depth)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * n_e2e / e2e_s
+    h2d = B * 144000 * 4
+    d2h = B * spec.num_species * 4 + B * 5 * 8 + B * 4
+
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the engine's stream ----
+    roof, stages = None, []
+    if rank == 0:
+        ctx.set_profiling(True)
+        acc = {}
+        reps = 5
+        for _ in range(reps):
+            ctx.run_device(d_audio.data_ptr(), B, True)
+            for name, ms in ctx.stage_times():
+                acc.setdefault(name, []).append(ms)
+        ctx.set_profiling(False)
+        st = [(n, float(np.mean(v))) for n, v in acc.items()]
+        dom, stages = _stage_roofline(spec, st, B, peaks)
+        if dom:
+            roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": None, "kernel": dom["stage"], "kernel_ms": dom["ms"],
+                    "share_of_step": dom["share"], "peak_source": peaks["src"] + (" sustained" if dom["bound"] == "tensor" else ""),
+                    "algorithmic_per_segment": dom["alg_per_segment"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, nseg, dt, _ = _cpu_oracle_rate(12.0, 8, 512)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{nseg} segments in batches of 8 ({dt:.1f} s), torch CPU FP32 oracle port; ORT CPU cannot run in this image"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BirdNET v2.4-like (random-init seed 0, build-authored graph) batch=256 via "
+                                   "BatchInferenceContext: front-end + CNN + fused top-k epilogue (BASELINE.json configs[1])",
+                       "global_batch": B * world, "segment_samples": 144000, "top_k": 5, "min_confidence": 0.1,
+                       "l2_policy": "inputs larger than L2 (147 MB batch > 126 MB L2)",
+                       "parallelism": f"{world} independent per-GPU shards, no collective",
+                       "precision_policy": "FP32-equivalent (see DESIGN.md)",
+                       "e2e_pipeline_depth": depth, "host_cores": os.cpu_count()},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step * K),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "stages": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in s.items()} for s in
+                       sorted(stages, key=lambda x: -x["ms"])[:12]],
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--pipeline-depth", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

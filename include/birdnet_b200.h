@@ -152,6 +152,11 @@ uint64_t bn_ctx_input_buffer_bytes(const bn_ctx* ctx); /* batch_context.rs:155-1
  * GPU (bench: inputs already in HBM).  fetch_outputs != 0 copies results to the pinned host slab. */
 int bn_ctx_run_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs,
                       const bn_run_opts* opts, bn_outputs* out);
+/* Asynchronous halves of bn_ctx_run_device: enqueue returns once the work is on the stream;
+ * several enqueues may be queued back to back (each overwrites the previous outputs); wait blocks
+ * (polling opts) until everything enqueued so far has finished and exposes the last outputs. */
+int bn_ctx_enqueue_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs);
+int bn_ctx_wait(bn_ctx* ctx, const bn_run_opts* opts, bn_outputs* out);
 /* Intermediate tensors of the last run, by ONNX value name ("spec", ...) — parity tests. */
 int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_elems, uint64_t* elems_out);
 int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems);

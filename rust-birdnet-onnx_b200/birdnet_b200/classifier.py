@@ -206,6 +206,18 @@ class BatchInferenceContext:
         raise_for_status(_lib.bn_ctx_stage_times(self._h, ms, C.cast(names, C.c_void_p), cap, C.byref(n)))
         return [(names[i].value.decode(), float(ms[i])) for i in range(min(n.value, cap))]
 
+    def enqueue_device(self, device_ptr: int, batch: int, fetch_outputs: bool = True) -> None:
+        raise_for_status(_lib.bn_ctx_enqueue_device(self._h, C.c_void_p(device_ptr), batch, 1 if fetch_outputs else 0))
+
+    def wait(self, options: Optional[InferenceOptions] = None):
+        ro, timeout = _run_opts(options)
+        out = _ffi.Outputs()
+        raise_for_status(_lib.bn_ctx_wait(self._h, C.byref(ro) if ro is not None else None, C.byref(out)), timeout)
+        return out
+
+    def stream_ptr(self) -> int:
+        return int(_lib.bn_ctx_stream(self._h) or 0)
+
     def run_device(self, device_ptr: int, batch: int, fetch_outputs: bool = True,
                    options: Optional[InferenceOptions] = None):
         """Run on a [batch, sample_count] FP32 buffer already resident on the engine's GPU."""

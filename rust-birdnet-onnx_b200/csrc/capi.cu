@@ -168,6 +168,12 @@ int bn_ctx_run_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t
     return ctx_run_device(ctx, d_audio, batch, fetch_outputs != 0, opts, out);
 }
 
+int bn_ctx_enqueue_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs) {
+    if (!d_audio && batch) return set_error(BN_ERR_INVALID_ARGUMENT, "null device buffer");
+    return ctx_enqueue_device(ctx, d_audio, batch, fetch_outputs != 0, nullptr);
+}
+int bn_ctx_wait(bn_ctx* ctx, const bn_run_opts* opts, bn_outputs* out) { return ctx_wait(ctx, opts, out); }
+
 int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_elems, uint64_t* elems_out) {
     if (!ctx || !name) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
     const Plan& p = ctx->eng->plan;

@@ -422,9 +422,9 @@ static int begin_run(bn_ctx* c, PostCfg& post, uint64_t& k_eff, const bn_run_opt
     return BN_OK;
 }
 
-int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts, bn_outputs* out) {
-    if (!c || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
-    if (batch == 0) { memset(out, 0, sizeof(*out)); return BN_OK; }
+int ctx_enqueue_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts) {
+    if (!c) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (batch == 0) return BN_OK;
     if (batch > c->max_batch)
         return set_error(BN_ERR_INFERENCE, "batch size " + std::to_string(batch) + " exceeds context max " + std::to_string(c->max_batch));
     PostCfg post;
@@ -436,15 +436,31 @@ int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, 
     if (fetch) { st = enqueue_fetch(c, (int)batch, k_eff); if (st != BN_OK) return st; }
     prof_mark(c, "end");
     BN_CUDA(cudaEventRecord(c->done, c->stream));
-    st = wait_done(c, opts);
+    c->pending_batch = batch;
+    c->pending_k = k_eff;
+    return BN_OK;
+}
+
+int ctx_wait(bn_ctx* c, const bn_run_opts* opts, bn_outputs* out) {
+    if (!c || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    BN_CUDA(cudaSetDevice(c->eng->device));
+    int st = wait_done(c, opts);
     if (st != BN_OK) return st;
-    fill_outputs(c, batch, k_eff, out);
+    fill_outputs(c, c->pending_batch, c->pending_k, out);
     if (c->profiling) {
         size_t n = c->prof_names.size();
         c->prof_ms.assign(n ? n - 1 : 0, 0.f);
         for (size_t i = 0; i + 1 < n; ++i) cudaEventElapsedTime(&c->prof_ms[i], c->prof_events[i], c->prof_events[i + 1]);
     }
     return BN_OK;
+}
+
+int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts, bn_outputs* out) {
+    if (!c || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (batch == 0) { memset(out, 0, sizeof(*out)); return BN_OK; }
+    int st = ctx_enqueue_device(c, d_audio, batch, fetch, opts);
+    if (st != BN_OK) return st;
+    return ctx_wait(c, opts, out);
 }
 
 // ---- host staging: gather caller slices into the pinned slab and ship them chunk by chunk ----

@@ -87,6 +87,7 @@ struct bn_ctx {
     uint64_t topk_cap = 0;       // slots per segment currently allocated
     std::shared_ptr<bn::RangeDev> range_in_flight;
     bool draining = false;
+    uint64_t pending_batch = 0, pending_k = 0;
     uint64_t last_launches = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -103,5 +104,7 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
                  bool check_max_first, const bn_run_opts* opts, bn_outputs* out);
 int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts,
                    bn_outputs* out);
+int ctx_enqueue_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts);
+int ctx_wait(bn_ctx* c, const bn_run_opts* opts, bn_outputs* out);
 int fill_io_info(const Plan& plan, bn_io_info* out);
 }  // namespace bn
