@@ -186,6 +186,16 @@ int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_e
         uint64_t n = std::min<uint64_t>(dst_elems, per * ctx->max_batch);
         BN_CUDA(cudaSetDevice(ctx->eng->device));
         BN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->eng->tc_mode && p.tensors[i].H * p.tensors[i].W > 1) {
+            // hi/lo fp16 planes -> FP32 (x = hi + lo)
+            const size_t plane = (size_t)std::max<uint64_t>(ctx->max_batch, 1) * per;
+            std::vector<__half> hi(n), lo(n);
+            const __half* base = reinterpret_cast<const __half*>(ctx->d_tensor[i]);
+            BN_CUDA(cudaMemcpy(hi.data(), base, n * sizeof(__half), cudaMemcpyDeviceToHost));
+            BN_CUDA(cudaMemcpy(lo.data(), base + plane, n * sizeof(__half), cudaMemcpyDeviceToHost));
+            for (uint64_t j = 0; j < n; ++j) dst[j] = __half2float(hi[j]) + __half2float(lo[j]);
+            return BN_OK;
+        }
         BN_CUDA(cudaMemcpy(dst, ctx->d_tensor[i], n * sizeof(float), cudaMemcpyDeviceToHost));
         return BN_OK;
     }

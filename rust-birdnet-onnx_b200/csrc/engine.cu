@@ -135,6 +135,15 @@ static void build_real_mel_basis(const SpecBranch& br, std::vector<float>& basis
     }
 }
 
+// UMMA N for a layer: the largest multiple of 16 (<= 256) that divides cout rounded up to 16
+static int choose_nt(int cout) {
+    const int c16 = (cout + 15) / 16 * 16;
+    int best = 16;
+    for (int nt = 16; nt <= 256; nt += 16)
+        if (c16 % nt == 0) best = nt;
+    return best;
+}
+
 // --------------------------------------------------------------------------------------
 // engine
 // --------------------------------------------------------------------------------------
@@ -162,6 +171,13 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
     if (prop.major < 10)
         return set_error(BN_ERR_RUNTIME_INIT, std::string("device '") + prop.name + "' is not sm_100-class; this engine is built for sm_100a only");
     BN_CUDA(init_kernels_for_device());
+    BN_CUDA(tc_conv_init_device());
+    const char* env_tc = getenv("BN_DISABLE_TC");
+    const bool tc_enabled = !(env_tc && env_tc[0] == '1');
+    e->tc_mode = tc_enabled;
+    e->num_sms = prop.multiProcessorCount;
+    const char* env_st = getenv("BN_TC_STAGES");
+    const int forced_stages = env_st ? atoi(env_st) : 0;
 
     Plan& p = e->plan;
     e->dev_ops.resize(p.ops.size());
@@ -172,6 +188,22 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
         BN_CUDA(cudaMemcpy(e->dev_ops[i].weight, op.weight.data(), op.weight.size() * sizeof(float), cudaMemcpyHostToDevice));
         BN_CUDA(cudaMalloc(&e->dev_ops[i].bias, op.bias.size() * sizeof(float)));
         BN_CUDA(cudaMemcpy(e->dev_ops[i].bias, op.bias.data(), op.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // dense contractions with >= 64 output channels (or any spatial conv) go to the tensor cores
+        const bool dense = op.kind == OP_CONV || (op.kind == OP_LINEAR && op.cout >= 64);
+        if (tc_enabled && dense && (op.cin % 8) == 0 && op.cout >= 16) {
+            DevOp& d = e->dev_ops[i];
+            const int K = op.k * op.k * op.cin;
+            d.nt = choose_nt(op.cout);
+            std::vector<uint16_t> pack;
+            tc_pack_weights(op.weight.data(), K, op.cout, op.ldw, d.nt, pack, &d.n_tiles, &d.k_chunks);
+            d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks);
+            while (d.stages > 2 && tc_conv_smem_bytes(d.nt, d.stages) > 208 * 1024) --d.stages;
+            d.tmem_cols = 32;
+            while (d.tmem_cols < 2 * d.nt) d.tmem_cols <<= 1;
+            BN_CUDA(cudaMalloc(&d.wpack, pack.size() * sizeof(uint16_t)));
+            BN_CUDA(cudaMemcpy(d.wpack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            d.use_tc = true;
+        }
         std::vector<float>().swap(op.weight);   // host copy no longer needed
     }
     if (p.fe.kind == FE_BIRDNET_V24) {
@@ -184,6 +216,34 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             BN_CUDA(cudaMemcpy(d, basis.data(), basis.size() * sizeof(float), cudaMemcpyHostToDevice));
             e->d_basis.push_back(d);
             e->ldb.push_back(ldb);
+            if (e->tc_mode) {
+                // A[t][k'] = Xp[t*row_stride + k'], k' = j*row_stride + c  <->  n = j*hop + c of the frame
+                bn_engine::FeTc ft;
+                ft.hop = br.hop;
+                ft.row_stride = (br.hop + 7) / 8 * 8;
+                const int J = ft.row_stride == br.hop ? 0 : (br.n_fft + br.hop - 1) / br.hop;
+                ft.K = J ? J * ft.row_stride : br.n_fft;
+                ft.rows = J ? br.n_frames + J - 1 : (p.sample_count + ft.row_stride - 1) / ft.row_stride + 1;
+                std::vector<float> wb((size_t)ft.K * ldb, 0.f);
+                for (int kp = 0; kp < ft.K; ++kp) {
+                    int n = kp;
+                    if (J) {
+                        const int j = kp / ft.row_stride, cc = kp - j * ft.row_stride;
+                        n = cc < br.hop ? j * br.hop + cc : -1;
+                    }
+                    if (n >= 0 && n < br.n_fft)
+                        for (int m = 0; m < br.n_mels; ++m) wb[(size_t)kp * ldb + m] = basis[(size_t)n * ldb + m];
+                }
+                ft.nt = choose_nt(br.n_mels);
+                std::vector<uint16_t> pack;
+                tc_pack_weights(wb.data(), ft.K, br.n_mels, ldb, ft.nt, pack, &ft.n_tiles, &ft.k_chunks);
+                ft.stages = tc_conv_pick_stages(ft.nt, ft.k_chunks);
+                ft.tmem_cols = 32;
+                while (ft.tmem_cols < 2 * ft.nt) ft.tmem_cols <<= 1;
+                BN_CUDA(cudaMalloc(&ft.wpack, pack.size() * sizeof(uint16_t)));
+                BN_CUDA(cudaMemcpy(ft.wpack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                e->fe_tc.push_back(ft);
+            }
         }
     } else {
         return set_error(BN_ERR_MODEL_LOAD, "log-mel front-end is not implemented in this engine build yet");
@@ -200,8 +260,10 @@ bn_engine::~bn_engine() {
     for (auto& d : dev_ops) {
         if (d.weight) cudaFree(d.weight);
         if (d.bias) cudaFree(d.bias);
+        if (d.wpack) cudaFree(d.wpack);
     }
     for (auto* b : d_basis) cudaFree(b);
+    for (auto& f : fe_tc) if (f.wpack) cudaFree(f.wpack);
 }
 
 bn_ctx::~bn_ctx() {
@@ -211,6 +273,7 @@ bn_ctx::~bn_ctx() {
     if (h_in) cudaFreeHost(h_in);
     if (d_in) cudaFree(d_in);
     if (d_norm) cudaFree(d_norm);
+    for (auto* x : d_xp) if (x) cudaFree(x);
     for (size_t i = 0; i < d_tensor.size(); ++i)
         if (d_tensor[i] && eng->plan.tensors[i].alias_of < 0 && eng->plan.tensors[i].scale_base < 0) cudaFree(d_tensor[i]);
     if (h_logits) cudaFreeHost(h_logits);
@@ -244,6 +307,11 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     memset(c->h_in, 0, mb * S * sizeof(float));    // vec![0.0f32; max*sample_count], batch_context.rs:122
     BN_CUDA(cudaMalloc(&c->d_in, mb * S * sizeof(float)));
     if (p.fe.normalize) BN_CUDA(cudaMalloc(&c->d_norm, mb * S * sizeof(float)));
+    for (auto& ft : e->fe_tc) {
+        __half* x = nullptr;
+        BN_CUDA(cudaMalloc(&x, 2 * mb * (size_t)ft.rows * ft.row_stride * sizeof(__half)));
+        c->d_xp.push_back(x);
+    }
     c->d_tensor.assign(p.tensors.size(), nullptr);
     for (size_t i = 0; i < p.tensors.size(); ++i) {
         const TensorInfo& t = p.tensors[i];
@@ -285,6 +353,100 @@ static void prof_mark(bn_ctx* c, const char* name) {
     c->prof_names.push_back(name);
 }
 
+
+// ---- tensor-core mode: spatial tensors are hi/lo fp16 planes, vectors ([B][C]) stay FP32 ------
+static inline bool is_spatial(const Plan& p, int t) { return p.tensors[t].H * p.tensors[t].W > 1; }
+static inline PlanesPtr planes_of(bn_ctx* c, int t) {
+    const Plan& p = c->eng->plan;
+    PlanesPtr r;
+    r.hi = reinterpret_cast<__half*>(c->d_tensor[t]);
+    r.plane = (size_t)std::max<uint64_t>(c->max_batch, 1) * p.tensors[p.root(t)].elems();
+    return r;
+}
+
+static void prof_mark(bn_ctx* c, const char* name);
+
+static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
+    bn_engine* e = c->eng;
+    const Plan& p = e->plan;
+    cudaStream_t s = c->stream;
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+        const PlanOp& op = p.ops[i];
+        const DevOp& d = e->dev_ops[i];
+        if (op.kind == OP_GAP) {
+            // squeeze fused into the preceding depthwise conv?
+            if (i > 0 && p.ops[i - 1].kind == OP_DWCONV && p.ops[i - 1].out == op.in) continue;
+            prof_mark(c, op.name.c_str());
+            BN_CUDA(launch_gap_planes(planes_of(c, op.in), c->d_tensor[op.out], B, op.hin * op.win, op.cin, s));
+            ++launches;
+            continue;
+        }
+        prof_mark(c, op.name.c_str());
+        if (op.kind == OP_DWCONV) {
+            float* pooled = nullptr;
+            if (i + 1 < p.ops.size() && p.ops[i + 1].kind == OP_GAP && p.ops[i + 1].in == op.out) pooled = c->d_tensor[p.ops[i + 1].out];
+            DwPlanesParams dp{planes_of(c, op.in), d.weight, d.bias, planes_of(c, op.out), pooled,
+                              B, op.hin, op.win, op.cout, op.hout, op.wout, op.k, op.stride, op.pad, op.act};
+            BN_CUDA(launch_dwconv_planes(dp, s));
+        } else if (d.use_tc) {
+            TcConvParams tp{};
+            const bool in_sp = is_spatial(p, op.in);
+            if (in_sp) {
+                PlanesPtr ip = planes_of(c, op.in);
+                tp.in_hi = ip.hi; tp.in_plane = ip.plane;
+                tp.in_mode = op.in_scale >= 0 ? TC_IN_PLANES_SCALED : TC_IN_PLANES;
+                tp.in_scale = op.in_scale >= 0 ? c->d_tensor[op.in_scale] : nullptr;
+            } else {
+                tp.in_f32 = c->d_tensor[op.in];
+                tp.in_mode = TC_IN_F32;
+                if (op.in_scale >= 0) return set_error(BN_ERR_INFERENCE, "gated vector input is not supported");
+            }
+            if (op.residual >= 0) {
+                if (!is_spatial(p, op.residual)) return set_error(BN_ERR_INFERENCE, "vector residual is not supported");
+                PlanesPtr rp = planes_of(c, op.residual);
+                tp.res_hi = rp.hi; tp.res_plane = rp.plane;
+            }
+            tp.bias = d.bias;
+            if (is_spatial(p, op.out)) {
+                PlanesPtr o = planes_of(c, op.out);
+                tp.out_hi = o.hi; tp.out_plane = o.plane;
+            } else {
+                tp.out_f32 = c->d_tensor[op.out];
+            }
+            tp.wpack = d.wpack;
+            tp.batch = B; tp.hin = op.hin; tp.win = op.win; tp.cin = op.cin;
+            tp.hout = op.hout; tp.wout = op.wout; tp.cout = op.cout;
+            tp.k = op.k; tp.stride = op.stride; tp.pad = op.pad; tp.act = op.act;
+            tp.K = op.k * op.k * op.cin;
+            tp.M = B * op.hout * op.wout;
+            tp.pix_stride = op.cin; tp.seg_stride = op.hin * op.win * op.cin; tp.tab_cin = op.cin;
+            tp.k_chunks = d.k_chunks; tp.n_tiles = d.n_tiles; tp.m_tiles = (tp.M + 127) / 128;
+            tp.nt = d.nt; tp.stages = d.stages; tp.tmem_cols = d.tmem_cols;
+            BN_CUDA(launch_tc_conv(tp, e->num_sms, s));
+        } else if (is_spatial(p, op.in) || is_spatial(p, op.out)) {
+            ConvPlanesParams cp{};
+            cp.in = planes_of(c, op.in);
+            cp.in_scale = op.in_scale >= 0 ? c->d_tensor[op.in_scale] : nullptr;
+            cp.weight = d.weight; cp.bias = d.bias;
+            if (op.residual >= 0) cp.residual = planes_of(c, op.residual);
+            cp.out = planes_of(c, op.out);
+            cp.batch = B; cp.hin = op.hin; cp.win = op.win; cp.cin = op.cin; cp.hout = op.hout; cp.wout = op.wout;
+            cp.cout = op.cout; cp.ldw = op.ldw; cp.k = op.k; cp.stride = op.stride; cp.pad = op.pad; cp.act = op.act;
+            if (op.cout <= 32 && (op.cout & 7) == 0 && op.in_scale < 0 && op.residual < 0 && op.cin <= 4)
+                BN_CUDA(launch_stem_planes(cp, s));
+            else
+                BN_CUDA(launch_conv_igemm_planes(cp, s));
+        } else {
+            ConvParams cp{c->d_tensor[op.in], op.in_scale >= 0 ? c->d_tensor[op.in_scale] : nullptr, d.weight, d.bias,
+                          op.residual >= 0 ? c->d_tensor[op.residual] : nullptr, c->d_tensor[op.out],
+                          B, op.hin, op.win, op.cin, op.hout, op.wout, op.cout, op.ldw, op.k, op.stride, op.pad, op.act};
+            BN_CUDA(launch_conv_igemm(cp, s));
+        }
+        ++launches;
+    }
+    return BN_OK;
+}
+
 // ---- the forward pass (device side), input already in c->d_in or `d_audio` -----------------
 static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg& post, uint64_t k_eff) {
     bn_engine* e = c->eng;
@@ -293,7 +455,19 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     uint64_t launches = 0;
     const float* fe_in = d_audio;
     prof_mark(c, "normalize");
-    if (p.fe.normalize) {
+    const bool fe_on_tc = e->tc_mode && !e->fe_tc.empty() && p.fe.normalize;
+    if (fe_on_tc) {
+        const size_t mb = std::max<uint64_t>(c->max_batch, 1);
+        FePlaneOut outs[2];
+        for (size_t bi = 0; bi < e->fe_tc.size(); ++bi) {
+            const auto& ft = e->fe_tc[bi];
+            outs[bi] = FePlaneOut{c->d_xp[bi], mb * (size_t)ft.rows * ft.row_stride, ft.hop, ft.row_stride, ft.rows};
+        }
+        BN_CUDA(launch_minmax_normalize_fe(d_audio, c->d_norm, outs, (int)e->fe_tc.size(), B, p.sample_count,
+                                           p.fe.eps, p.fe.half, p.fe.two, s));
+        ++launches;
+        fe_in = c->d_norm;
+    } else if (p.fe.normalize) {
         BN_CUDA(launch_minmax_normalize(d_audio, c->d_norm, B, p.sample_count, p.fe.eps, p.fe.half, p.fe.two, s));
         ++launches;
         fe_in = c->d_norm;
@@ -302,10 +476,37 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     for (size_t bi = 0; bi < p.fe.branches.size(); ++bi) {
         const SpecBranch& br = p.fe.branches[bi];
         prof_mark(c, bi == 0 ? "spectrogram0" : "spectrogram1");
-        BN_CUDA(launch_spectrogram_v24(fe_in, e->d_basis[bi], e->ldb[bi], spec, B, p.sample_count, br.n_fft, br.hop,
-                                       br.n_frames, br.n_mels, (int)p.fe.branches.size(), (int)bi, br.exponent, s));
+        if (fe_on_tc) {
+            const auto& ft = e->fe_tc[bi];
+            const size_t mb = std::max<uint64_t>(c->max_batch, 1);
+            PlanesPtr o = planes_of(c, p.fe.out_tensor);
+            TcConvParams tp{};
+            tp.in_hi = c->d_xp[bi];
+            tp.in_plane = mb * (size_t)ft.rows * ft.row_stride;
+            tp.in_mode = TC_IN_PLANES;
+            tp.out_hi = o.hi; tp.out_plane = o.plane;
+            tp.spec_nframes = br.n_frames; tp.spec_nch = (int)p.fe.branches.size(); tp.spec_ch = (int)bi;
+            tp.spec_exponent = br.exponent;
+            tp.wpack = ft.wpack;
+            tp.batch = B; tp.hin = 1; tp.win = br.n_frames; tp.cin = ft.K; tp.hout = 1; tp.wout = br.n_frames;
+            tp.cout = br.n_mels; tp.k = 1; tp.stride = 1; tp.pad = 0; tp.act = ACT_NONE;
+            tp.K = ft.K; tp.M = B * br.n_frames; tp.k_chunks = ft.k_chunks; tp.n_tiles = ft.n_tiles;
+            tp.m_tiles = (tp.M + 127) / 128;
+            tp.pix_stride = ft.row_stride; tp.seg_stride = ft.rows * ft.row_stride; tp.tab_cin = ft.K;
+            tp.nt = ft.nt; tp.stages = ft.stages; tp.tmem_cols = ft.tmem_cols;
+            BN_CUDA(launch_tc_conv(tp, e->num_sms, s));
+        } else if (e->tc_mode)
+            BN_CUDA(launch_spectrogram_v24_planes(fe_in, e->d_basis[bi], e->ldb[bi], planes_of(c, p.fe.out_tensor), B, p.sample_count,
+                                                  br.n_fft, br.hop, br.n_frames, br.n_mels, (int)p.fe.branches.size(), (int)bi, br.exponent, s));
+        else
+            BN_CUDA(launch_spectrogram_v24(fe_in, e->d_basis[bi], e->ldb[bi], spec, B, p.sample_count, br.n_fft, br.hop,
+                                           br.n_frames, br.n_mels, (int)p.fe.branches.size(), (int)bi, br.exponent, s));
         ++launches;
     }
+    if (e->tc_mode) {
+        int st = enqueue_ops_tc(c, B, launches);
+        if (st != BN_OK) return st;
+    } else {
     for (size_t i = 0; i < p.ops.size(); ++i) {
         const PlanOp& op = p.ops[i];
         prof_mark(c, op.name.c_str());
@@ -323,6 +524,7 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
             BN_CUDA(launch_conv_igemm(cp, s));
         }
         ++launches;
+    }
     }
     prof_mark(c, "topk_epilogue");
     TopkParams tp{};

@@ -13,6 +13,7 @@
 #include "../../include/birdnet_b200.h"
 #include "kernels.h"
 #include "plan.h"
+#include "tc_conv.h"
 
 namespace bn {
 
@@ -31,8 +32,12 @@ int load_plan(const char* path, int override_type, Plan& plan);
     } while (0)
 
 struct DevOp {
-    float* weight = nullptr;
+    float* weight = nullptr;     // FP32 engine layout (CUDA-core kernels)
     float* bias = nullptr;
+    // tensor-core path (tc_conv.cu)
+    bool use_tc = false;
+    void* wpack = nullptr;
+    int nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32;
 };
 
 struct RangeDev {   // dense per-class tri-state on the device
@@ -56,11 +61,16 @@ struct PostCfg {
 struct bn_engine {
     int device = 0;
     int pack_threads = 0;
+    bool tc_mode = true;          // tensor-core path with hi/lo-plane activations (BN_DISABLE_TC=1 -> FP32 CUDA-core path)
+    int num_sms = 148;
     bn::Plan plan;
     bn_io_info info{};
     std::vector<bn::DevOp> dev_ops;
     std::vector<float*> d_basis;   // per front-end branch [n_fft][ldb]
     std::vector<int> ldb;
+    // tensor-core front-end: per branch the block-Toeplitz frame matrix geometry + packed basis
+    struct FeTc { void* wpack = nullptr; int hop = 0, row_stride = 0, rows = 0, K = 0, nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32; };
+    std::vector<FeTc> fe_tc;
     std::mutex post_mu;
     bn::PostCfg post;
     std::mutex ctx_mu;
@@ -77,6 +87,7 @@ struct bn_ctx {
     float* h_in = nullptr;       // pinned [max_batch][S]
     float* d_in = nullptr;       // [max_batch][S]
     float* d_norm = nullptr;     // [max_batch][S] normalised audio (v2.4 front-end)
+    std::vector<__half*> d_xp;   // per branch: hi/lo planes of the frame matrix [max_batch][rows][row_stride]
     std::vector<float*> d_tensor;   // per plan tensor (aliases resolved to their root)
     float* h_logits = nullptr;   // pinned
     float* h_emb = nullptr;      // pinned

@@ -71,6 +71,96 @@ cudaError_t launch_minmax_normalize(const float* x, float* y, int batch, int sam
     return cudaGetLastError();
 }
 
+struct FeOuts { FePlaneOut o[2]; int n; };
+
+__global__ void __launch_bounds__(1024) k_minmax_normalize_fe(const float* __restrict__ x, float* __restrict__ y, FeOuts fo,
+                                                              int S, float eps, float half, float two) {
+    const float* xs = x + (size_t)blockIdx.x * S;
+    float* ys = y ? y + (size_t)blockIdx.x * S : nullptr;
+    const int n4 = S >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(xs);
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        float4 v = x4[i];
+        mn = nan_min(nan_min(mn, v.x), nan_min(nan_min(v.y, v.z), v.w));
+        mx = nan_max(nan_max(mx, v.x), nan_max(nan_max(v.y, v.z), v.w));
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < S; i += blockDim.x) {
+        mn = nan_min(mn, xs[i]);
+        mx = nan_max(mx, xs[i]);
+    }
+    __shared__ float s_mn[32], s_mx[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int nw = blockDim.x >> 5;
+        mn = threadIdx.x < nw ? s_mn[threadIdx.x] : INFINITY;
+        mx = threadIdx.x < nw ? s_mx[threadIdx.x] : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (threadIdx.x == 0) { s_mn[0] = mn; s_mx[0] = mx; }
+    }
+    __syncthreads();
+    const float lo = s_mn[0];
+    const float den = __fadd_rn(__fsub_rn(s_mx[0], lo), eps);
+    if (ys) {
+        float4* y4 = reinterpret_cast<float4*>(ys);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 v = x4[i], r;
+            r.x = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.x, lo), den), half), two);
+            r.y = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.y, lo), den), half), two);
+            r.z = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.z, lo), den), half), two);
+            r.w = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.w, lo), den), half), two);
+            y4[i] = r;
+        }
+        for (int i = (n4 << 2) + threadIdx.x; i < S; i += blockDim.x)
+            ys[i] = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(xs[i], lo), den), half), two);
+    }
+    for (int bi = 0; bi < fo.n; ++bi) {
+        const FePlaneOut o = fo.o[bi];
+        const int units_per_row = o.row_stride >> 3;
+        const int n_units = o.rows * units_per_row;
+        __half* hi = o.hi + (size_t)blockIdx.x * o.rows * o.row_stride;
+        for (int u = threadIdx.x; u < n_units; u += blockDim.x) {
+            const int r = u / units_per_row, c0 = (u - r * units_per_row) << 3;
+            __half2 h[4], l[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                float v[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + 2 * e2 + q;
+                    const int src = r * o.hop + c;
+                    v[q] = (c < o.hop && src < S)
+                               ? __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(xs[src], lo), den), half), two) : 0.f;
+                }
+                h[e2] = __floats2half2_rn(v[0], v[1]);
+                float2 bk = __half22float2(h[e2]);
+                l[e2] = __floats2half2_rn(v[0] - bk.x, v[1] - bk.y);
+            }
+            *reinterpret_cast<uint4*>(hi + (size_t)u * 8) = *reinterpret_cast<uint4*>(h);
+            *reinterpret_cast<uint4*>(hi + o.plane + (size_t)u * 8) = *reinterpret_cast<uint4*>(l);
+        }
+    }
+}
+
+cudaError_t launch_minmax_normalize_fe(const float* x, float* y, const FePlaneOut* outs, int n_outs, int batch,
+                                       int sample_count, float eps, float half, float two, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    if (n_outs > 2) return cudaErrorInvalidValue;
+    FeOuts fo{};
+    fo.n = n_outs;
+    for (int i = 0; i < n_outs; ++i) fo.o[i] = outs[i];
+    k_minmax_normalize_fe<<<batch, 1024, 0, stream>>>(x, y, fo, sample_count, eps, half, two);
+    return cudaGetLastError();
+}
+
 // ======================================================================================
 // Generic FP32 implicit GEMM: C[M][N] = A[M][K] * W[K][ldw], A supplied by a loader functor
 // ======================================================================================
@@ -200,6 +290,93 @@ struct SpecEpilogueV24 {
     }
 };
 
+// ---- planes variants of the loaders / epilogues -------------------------------------------
+__device__ __forceinline__ void split_store(__half* hi, size_t plane, size_t o, float v) {
+    __half h = __float2half_rn(v);
+    hi[o] = h;
+    hi[plane + o] = __float2half_rn(v - __half2float(h));
+}
+__device__ __forceinline__ float planes_load(const __half* hi, size_t plane, size_t o) {
+    return __half2float(hi[o]) + __half2float(hi[plane + o]);
+}
+
+struct ConvLoaderPlanes {
+    const __half* in;
+    size_t plane;
+    const float* in_scale;
+    int hin, win, cin, hout, wout, k, stride, pad;
+    struct Row {
+        size_t base;
+        const float* scale;
+        int iy0, ix0;
+        bool valid;
+    };
+    __device__ Row row(int m, int M) const {
+        Row r;
+        r.valid = m < M;
+        int mm = r.valid ? m : 0;
+        int hw = hout * wout;
+        int b = mm / hw, rem = mm - b * hw;
+        int oy = rem / wout, ox = rem - oy * wout;
+        r.iy0 = oy * stride - pad;
+        r.ix0 = ox * stride - pad;
+        r.base = (size_t)b * hin * win * cin;
+        r.scale = in_scale ? in_scale + (size_t)b * cin : nullptr;
+        return r;
+    }
+    __device__ void load4(const Row& r, int kidx, int K, float v[4]) const {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = 0.f;
+            int kk = kidx + j;
+            if (!r.valid || kk >= K) continue;
+            int tap = kk / cin, ci = kk - tap * cin;
+            int ky = tap / k, kx = tap - ky * k;
+            int iy = r.iy0 + ky, ix = r.ix0 + kx;
+            if (iy < 0 || iy >= hin || ix < 0 || ix >= win) continue;
+            float t = planes_load(in, plane, r.base + ((size_t)iy * win + ix) * cin + ci);
+            if (r.scale) t *= r.scale[ci];
+            v[j] = t;
+        }
+    }
+};
+
+struct ConvEpiloguePlanes {
+    const float* bias;
+    const __half* res;
+    size_t res_plane;
+    __half* out;
+    size_t out_plane;
+    int cout, act;
+    __device__ void store4(int m, int n, const float a[4], int N) const {
+        size_t o = (size_t)m * cout + n;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (n + j >= N) break;
+            float v = apply_act(a[j] + bias[n + j], act);
+            if (res) v += planes_load(res, res_plane, o + j);
+            split_store(out, out_plane, o + j, v);
+        }
+    }
+};
+
+struct SpecEpilogueV24Planes {
+    __half* spec;
+    size_t plane;
+    int n_frames, n_mels, n_ch, ch;
+    float exponent;
+    __device__ void store4(int m, int n, const float a[4], int N) const {
+        int b = m / n_frames, t = m - b * n_frames;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (n + j >= N) break;
+            float p = a[j] * a[j];
+            float v = p > 0.f ? powf(p, exponent) : (p == 0.f ? 0.f : p);
+            split_store(spec, plane, (((size_t)b * n_mels + (n + j)) * n_frames + t) * n_ch + ch, v);
+        }
+    }
+};
+
 template <class Loader, class Epilogue>
 __global__ void __launch_bounds__(256) k_igemm_f32(Loader ld, Epilogue ep, const float* __restrict__ W,
                                                    int ldw, int M, int N, int K) {
@@ -266,6 +443,210 @@ cudaError_t launch_spectrogram_v24(const float* xnorm, const float* basis, int l
     SpecEpilogueV24 ep{spec, n_frames, n_mels, n_ch, ch, exponent};
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((n_mels + BN - 1) / BN));
     k_igemm_f32<<<grid, 256, 0, stream>>>(ld, ep, basis, ldb, (int)M, n_mels, n_fft);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_igemm_planes(const ConvPlanesParams& p, cudaStream_t stream) {
+    const long long M = (long long)p.batch * p.hout * p.wout;
+    if (M <= 0) return cudaSuccess;
+    const int K = p.k * p.k * p.cin, N = p.cout;
+    ConvLoaderPlanes ld{p.in.hi, p.in.plane, p.in_scale, p.hin, p.win, p.cin, p.hout, p.wout, p.k, p.stride, p.pad};
+    ConvEpiloguePlanes ep{p.bias, p.residual.hi, p.residual.plane, p.out.hi, p.out.plane, p.cout, p.act};
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    k_igemm_f32<<<grid, 256, 0, stream>>>(ld, ep, p.weight, p.ldw, (int)M, N, K);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_spectrogram_v24_planes(const float* xnorm, const float* basis, int ldb, PlanesPtr spec,
+                                          int batch, int sample_count, int n_fft, int hop, int n_frames,
+                                          int n_mels, int n_ch, int ch, float exponent, cudaStream_t stream) {
+    const long long M = (long long)batch * n_frames;
+    if (M <= 0) return cudaSuccess;
+    FrameLoader ld{xnorm, sample_count, hop, n_frames};
+    SpecEpilogueV24Planes ep{spec.hi, spec.plane, n_frames, n_mels, n_ch, ch, exponent};
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((n_mels + BN - 1) / BN));
+    k_igemm_f32<<<grid, 256, 0, stream>>>(ld, ep, basis, ldb, (int)M, n_mels, n_fft);
+    return cudaGetLastError();
+}
+
+// ======================================================================================
+// Depthwise conv on planes.  One CTA per (segment, group of CG channels): the whole input
+// patch of the group is staged in shared memory as FP32 (hi + lo) with 16-byte loads, every
+// thread then owns one channel and a strided set of output pixels.  The global average of the
+// activated output (the squeeze of squeeze-excite) is reduced in a fixed order -> deterministic.
+// ======================================================================================
+template <int CG>
+__global__ void __launch_bounds__(256) k_dwconv_planes(DwPlanesParams p) {
+    extern __shared__ __align__(16) float s_in[];          // [hin*win][CG]
+    __shared__ float s_part[256];
+    constexpr int PG = 256 / CG;                            // pixel groups
+    const int cgroups = p.c / CG;
+    const int b = blockIdx.x / cgroups, cg = blockIdx.x - b * cgroups;
+    const int c0 = cg * CG;
+    const int npin = p.hin * p.win, npout = p.hout * p.wout;
+    const size_t in_base = (size_t)b * npin * p.c + c0;
+    // stage: CG/8 16-byte units per pixel and plane
+    constexpr int UPP = CG / 8;
+    for (int u = threadIdx.x; u < npin * UPP; u += 256) {
+        const int pix = u / UPP, cu = u - pix * UPP;
+        const size_t o = in_base + (size_t)pix * p.c + cu * 8;
+        uint4 qh = __ldg(reinterpret_cast<const uint4*>(p.in.hi + o));
+        uint4 ql = __ldg(reinterpret_cast<const uint4*>(p.in.hi + p.in.plane + o));
+        const __half2* h = reinterpret_cast<const __half2*>(&qh);
+        const __half2* l = reinterpret_cast<const __half2*>(&ql);
+        float* dst = s_in + (size_t)pix * CG + cu * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 a = __half22float2(h[i]), d = __half22float2(l[i]);
+            dst[2 * i] = a.x + d.x;
+            dst[2 * i + 1] = a.y + d.y;
+        }
+    }
+    const int cl = threadIdx.x % CG, pg = threadIdx.x / CG;
+    const int c = c0 + cl;
+    float wreg[25];
+    const int k2 = p.k * p.k;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) wreg[i] = i < k2 ? p.weight[(size_t)i * p.c + c] : 0.f;
+    const float bias = p.bias[c];
+    __syncthreads();
+    float pool = 0.f;
+    for (int pix = pg; pix < npout; pix += PG) {
+        const int oy = pix / p.wout, ox = pix - oy * p.wout;
+        const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+        float acc = bias;
+        if (p.k == 3) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = iy0 + ky;
+                if (iy < 0 || iy >= p.hin) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ix0 + kx;
+                    if (ix < 0 || ix >= p.win) continue;
+                    acc = fmaf(s_in[(size_t)(iy * p.win + ix) * CG + cl], wreg[ky * 3 + kx], acc);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+                const int iy = iy0 + ky;
+                if (ky >= p.k || iy < 0 || iy >= p.hin) continue;
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int ix = ix0 + kx;
+                    if (kx >= p.k || ix < 0 || ix >= p.win) continue;
+                    acc = fmaf(s_in[(size_t)(iy * p.win + ix) * CG + cl], wreg[ky * p.k + kx], acc);
+                }
+            }
+        }
+        acc = apply_act(acc, p.act);
+        split_store(p.out.hi, p.out.plane, ((size_t)b * npout + pix) * p.c + c, acc);
+        pool += acc;
+    }
+    if (p.pooled) {
+        s_part[threadIdx.x] = pool;
+        __syncthreads();
+        if (threadIdx.x < CG) {
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < PG; ++g) s += s_part[g * CG + threadIdx.x];
+            p.pooled[(size_t)b * p.c + c0 + threadIdx.x] = s / (float)npout;
+        }
+    }
+}
+
+cudaError_t launch_dwconv_planes(const DwPlanesParams& p, cudaStream_t stream) {
+    if (p.batch <= 0) return cudaSuccess;
+    if (p.k * p.k > 25 || (p.c & 15)) return cudaErrorInvalidValue;
+    const int npin = p.hin * p.win;
+    // largest channel group whose FP32 patch fits in ~96 KB of shared memory
+    int cg = 64;
+    while (cg > 16 && ((p.c % cg) != 0 || (size_t)npin * cg * 4 > 96 * 1024)) cg >>= 1;
+    if ((p.c % cg) != 0 || (size_t)npin * cg * 4 > 200 * 1024) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)npin * cg * 4;
+    const int grid = p.batch * (p.c / cg);
+    if (cg == 64) k_dwconv_planes<64><<<grid, 256, smem, stream>>>(p);
+    else if (cg == 32) k_dwconv_planes<32><<<grid, 256, smem, stream>>>(p);
+    else k_dwconv_planes<16><<<grid, 256, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ======================================================================================
+// Stem: direct k x k conv for tiny Cin (the 2-channel spectrogram), planes in / planes out.
+// One thread per output pixel computes all Cout (<= 32) channels; weights live in smem.
+// ======================================================================================
+__global__ void __launch_bounds__(128) k_stem_planes(ConvPlanesParams p, int K) {
+    extern __shared__ float s_w[];                          // [K][cout] then bias[cout]
+    for (int i = threadIdx.x; i < K * p.cout; i += blockDim.x) s_w[i] = p.weight[(size_t)(i / p.cout) * p.ldw + (i % p.cout)];
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_w[K * p.cout + i] = p.bias[i];
+    __syncthreads();
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long M = (long long)p.batch * p.hout * p.wout;
+    if (m >= M) return;
+    const int hw = p.hout * p.wout;
+    const int b = (int)(m / hw), rem = (int)(m - (long long)b * hw);
+    const int oy = rem / p.wout, ox = rem - oy * p.wout;
+    float acc[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) acc[n] = n < p.cout ? s_w[K * p.cout + n] : 0.f;
+    const size_t in_base = (size_t)b * p.hin * p.win * p.cin;
+    for (int ky = 0; ky < p.k; ++ky) {
+        const int iy = oy * p.stride - p.pad + ky;
+        if (iy < 0 || iy >= p.hin) continue;
+        for (int kx = 0; kx < p.k; ++kx) {
+            const int ix = ox * p.stride - p.pad + kx;
+            if (ix < 0 || ix >= p.win) continue;
+            const size_t o = in_base + ((size_t)iy * p.win + ix) * p.cin;
+            for (int ci = 0; ci < p.cin; ++ci) {
+                const float x = planes_load(p.in.hi, p.in.plane, o + ci);
+                const float* w = s_w + (size_t)((ky * p.k + kx) * p.cin + ci) * p.cout;
+#pragma unroll
+                for (int n = 0; n < 32; ++n)
+                    if (n < p.cout) acc[n] = fmaf(x, w[n], acc[n]);
+            }
+        }
+    }
+    const size_t oo = (size_t)m * p.cout;
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8) {
+        if (n8 * 8 >= p.cout) break;
+        __half2 h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a = apply_act(acc[n8 * 8 + 2 * i], p.act), d = apply_act(acc[n8 * 8 + 2 * i + 1], p.act);
+            h[i] = __floats2half2_rn(a, d);
+            float2 bk = __half22float2(h[i]);
+            l[i] = __floats2half2_rn(a - bk.x, d - bk.y);
+        }
+        *reinterpret_cast<uint4*>(p.out.hi + oo + n8 * 8) = *reinterpret_cast<uint4*>(h);
+        *reinterpret_cast<uint4*>(p.out.hi + p.out.plane + oo + n8 * 8) = *reinterpret_cast<uint4*>(l);
+    }
+}
+
+cudaError_t launch_stem_planes(const ConvPlanesParams& p, cudaStream_t stream) {
+    const long long M = (long long)p.batch * p.hout * p.wout;
+    if (M <= 0) return cudaSuccess;
+    if (p.cout > 32 || (p.cout & 7) || p.in_scale || p.residual.hi) return cudaErrorInvalidValue;
+    const int K = p.k * p.k * p.cin;
+    const size_t smem = ((size_t)K * p.cout + p.cout) * sizeof(float);
+    k_stem_planes<<<(unsigned)((M + 127) / 128), 128, smem, stream>>>(p, K);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128) k_gap_planes(const __half* __restrict__ in, size_t plane, float* __restrict__ out, int hw, int c) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const size_t base = (size_t)blockIdx.y * hw * c + ch;
+    float s = 0.f;
+    for (int i = 0; i < hw; ++i) s += planes_load(in, plane, base + (size_t)i * c);
+    out[(size_t)blockIdx.y * c + ch] = s / (float)hw;
+}
+
+cudaError_t launch_gap_planes(PlanesPtr in, float* out, int batch, int hw, int c, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    dim3 grid((c + 127) / 128, batch);
+    k_gap_planes<<<grid, 128, 0, stream>>>(in.hi, in.plane, out, hw, c);
     return cudaGetLastError();
 }
 
@@ -489,6 +870,9 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 constexpr int kMaxSortSmem = 220 * 1024;
 
 cudaError_t init_kernels_for_device() {
+    cudaFuncSetAttribute(k_dwconv_planes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dwconv_planes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dwconv_planes<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaError_t e = cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSortSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_range_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSortSmem);

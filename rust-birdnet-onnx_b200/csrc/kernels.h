@@ -1,6 +1,7 @@
 // Launchers for the sm_100a kernels of the hot path.  All tensors are NHWC FP32 in HBM.
 // Every launcher enqueues on `stream` and returns the cudaError_t of the launch.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -48,6 +49,49 @@ cudaError_t launch_dwconv(const DwParams& p, cudaStream_t stream);
 
 // global average pool: [B][hw][c] -> [B][c]
 cudaError_t launch_gap(const float* in, float* out, int batch, int hw, int c, cudaStream_t stream);
+
+// ---- "planes" storage variants (hi/lo fp16 planes, see tc_conv.h) ----------------------
+struct PlanesPtr {
+    __half* hi;        // lo = hi + plane
+    size_t plane;
+};
+// normaliser that also emits, per spectrogram branch, the fp16 hi/lo "frame matrix" the
+// tensor-core front-end GEMM reads: Xp[b][r][c] = y[r*hop + c] (c < hop, inside the segment) else 0,
+// rows of row_stride = round_up(hop, 8) elements so every row start is 16-byte aligned and frame t
+// is the contiguous run Xp[t*row_stride ...] (block-Toeplitz form of the overlapping frames).
+struct FePlaneOut {
+    __half* hi;
+    size_t plane;       // lo = hi + plane
+    int hop, row_stride, rows;
+};
+cudaError_t launch_minmax_normalize_fe(const float* x, float* y, const FePlaneOut* outs, int n_outs, int batch,
+                                       int sample_count, float eps, float half, float two, cudaStream_t stream);
+// framed DFT x mel -> square -> pow, written as planes
+cudaError_t launch_spectrogram_v24_planes(const float* xnorm, const float* basis, int ldb, PlanesPtr spec,
+                                          int batch, int sample_count, int n_fft, int hop, int n_frames,
+                                          int n_mels, int n_ch, int ch, float exponent, cudaStream_t stream);
+struct ConvPlanesParams {
+    PlanesPtr in;
+    const float* in_scale;
+    const float* weight;
+    const float* bias;
+    PlanesPtr residual;   // hi == nullptr -> none
+    PlanesPtr out;
+    int batch, hin, win, cin, hout, wout, cout, ldw, k, stride, pad, act;
+};
+cudaError_t launch_conv_igemm_planes(const ConvPlanesParams& p, cudaStream_t stream);
+// direct conv for tiny Cin (stem): cout <= 32, no gate / residual
+cudaError_t launch_stem_planes(const ConvPlanesParams& p, cudaStream_t stream);
+struct DwPlanesParams {
+    PlanesPtr in;
+    const float* weight;  // [k*k][c]
+    const float* bias;
+    PlanesPtr out;
+    float* pooled;        // [B][c] global average of the output (fused squeeze), or nullptr
+    int batch, hin, win, c, hout, wout, k, stride, pad, act;
+};
+cudaError_t launch_dwconv_planes(const DwPlanesParams& p, cudaStream_t stream);
+cudaError_t launch_gap_planes(PlanesPtr in, float* out, int batch, int hw, int c, cudaStream_t stream);
 
 // ---- epilogue (rows A4 / A6) ------------------------------------------------------
 struct TopkParams {

@@ -1,0 +1,417 @@
+// Implicit-GEMM convolution / dense layer on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+//   D[M = B*Hout*Wout][N = Cout] = A[M][K = k*k*Cin] * W[K][N]      (+bias, activation, +residual)
+//
+// Precision policy "FP32-equivalent": operands are fp16 hi + fp16 lo pairs (x = hi + lo to ~22
+// bits) and every K step issues three kind::f16 MMAs (hi*hi + hi*lo + lo*hi) into one FP32 TMEM
+// accumulator; the dropped lo*lo term is ~2^-22 relative.  See DESIGN.md "precision policy".
+//
+// Persistent, warp-specialised CTA (288 threads, one per SM), static round-robin tile schedule:
+//   warps 0-3  A producers: im2col gather of the 128-row tile straight from the hi/lo planes with
+//              16-byte cp.async (zero-fill for padding) into SWIZZLE_128B K-major smem; thread 0
+//              also issues one 1-D bulk copy (TMA engine) per K chunk for the pre-swizzled weights
+//   warp  4    owns TMEM; lane 0 issues tcgen05.mma and commits stage/accumulator barriers
+//   warps 5-8  epilogue: tcgen05.ld -> bias / SiLU / sigmoid / residual -> split -> global planes
+// Two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+// smem ring: STAGES x { A_hi 16 KB | A_lo 16 KB | W_hi NT*128 B | W_lo NT*128 B }.
+#include "tc_common.cuh"
+#include "tc_conv.h"
+
+namespace bn {
+using namespace tc;
+
+constexpr int TM = 128;           // UMMA M (one TMEM lane per output row)
+constexpr int KC = 64;            // K elements per smem stage = one 128-byte swizzle row of fp16
+constexpr int MAX_STAGES = 6;
+constexpr int MAX_K_CHUNKS = 64;     // K <= 4096
+constexpr int MAX_SMEM_BIAS = 1536;
+constexpr int A_TILE_BYTES = TM * 128;
+constexpr int NTHREADS = 288;
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+    if (act == KACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+    if (act == KACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+    return v;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void unpack8(const uint4& q, float v[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) k_tc_conv(TcConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ uint32_t tmem_holder;
+    __shared__ int2 tap_tab[MAX_K_CHUNKS * 8];
+    __shared__ float s_bias[MAX_SMEM_BIAS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NT = p.nt, STAGES = p.stages;
+    const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)NT * 128u;
+    const uint32_t w_bytes = 2u * (uint32_t)NT * 128u;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 129);      // 128 producer threads + thread 0's expect_tx arrive
+            mbar_init(&bar_empty[s], 1);       // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_acc_full[a], 1);    // tcgen05.commit
+            mbar_init(&bar_acc_empty[a], 4);   // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_holder, p.tmem_cols);
+    // K unit -> (tap element offset, tap bit) table, shared by all tiles of this CTA
+    for (int u = tid; u < p.k_chunks * 8; u += NTHREADS) {
+        const int k0 = u * 8;
+        int2 e;
+        if (k0 < p.K) {
+            const int tap = k0 / p.tab_cin, ci = k0 - tap * p.tab_cin;
+            const int ky = tap / p.k, kx = tap - ky * p.k;
+            e.x = (ky * p.win + kx) * p.pix_stride + ci;
+            e.y = tap;
+        } else {
+            e.x = 0;
+            e.y = 31;                              // never set in a row mask -> zero fill
+        }
+        tap_tab[u] = e;
+    }
+    const bool s_bias_ok = p.bias != nullptr && p.cout <= MAX_SMEM_BIAS;
+    if (s_bias_ok)
+        for (int i = tid; i < p.cout; i += NTHREADS) s_bias[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    if (warp < 4) {
+        // ================================ A / W producers ================================
+        // Per thread: one 16-byte K unit (8 channels) of 8 rows (rbase + 16*i).  Everything that
+        // does not depend on the K chunk is hoisted to tile setup: per row a 32-bit element offset
+        // of tap (0,0) and a bit mask of the taps that fall inside the image; per (chunk, unit) the
+        // tap's element offset and bit index come from the smem table built above.
+        const int unit = tid & 7;
+        const int rbase = tid >> 3;
+        const int hw = p.hout * p.wout;
+        const uint32_t dst0 = sw128_offset((uint32_t)rbase, (uint32_t)unit);   // row i: + i*2048
+        uint32_t s = 0, ph = 0;                // ring slot / phase of the chunk being issued
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m0 = (t / p.n_tiles) * TM;
+            const int n_tile = t - (t / p.n_tiles) * p.n_tiles;
+            int32_t pix_off[8];                // element offset of input pixel (iy0, ix0), channel 0
+            uint32_t tmask[8];                 // bit (ky*k + kx) set <=> tap inside the image
+            uint32_t seg_idx[8];
+            {
+                int m = m0 + rbase;
+                int b = m / hw, rem = m - b * hw;
+                int oy = rem / p.wout, ox = rem - oy * p.wout;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (m + 16 * i < p.M) {
+                        const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+                        uint32_t xm = 0, mk = 0;
+                        for (int kx = 0; kx < p.k; ++kx) xm |= (uint32_t)(ix0 + kx >= 0 && ix0 + kx < p.win) << kx;
+                        for (int ky = 0; ky < p.k; ++ky)
+                            if (iy0 + ky >= 0 && iy0 + ky < p.hin) mk |= xm << (ky * p.k);
+                        tmask[i] = mk;
+                        pix_off[i] = b * p.seg_stride + (iy0 * p.win + ix0) * p.pix_stride;
+                        seg_idx[i] = (uint32_t)b;
+                    } else {
+                        tmask[i] = 0; pix_off[i] = 0; seg_idx[i] = 0;
+                    }
+                    ox += 16;
+                    while (ox >= p.wout) { ox -= p.wout; ++oy; }
+                    while (oy >= p.hout) { oy -= p.hout; ++b; }
+                }
+            }
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                mbar_wait(&bar_empty[s], ph ^ 1u);
+                uint8_t* st = tiles + (size_t)s * stage_bytes;
+                if (tid == 0) {
+                    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
+                                 ::"r"(smem_u32(&bar_full[s])), "r"(w_bytes) : "memory");
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
+                                         ((size_t)n_tile * p.k_chunks + kc) * w_bytes;
+                    bulk_copy_g2s(st + 2 * A_TILE_BYTES, src, w_bytes, &bar_full[s]);
+                }
+                const int2 te = tap_tab[kc * 8 + unit];   // x: element offset of (tap, ci); y: tap bit (31 = beyond K)
+                if (MODE == TC_IN_PLANES) {
+                    const uint32_t d = smem_u32(st) + dst0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = (tmask[i] >> te.y) & 1u;
+                        const __half* src = ok ? p.in_hi + (pix_off[i] + te.x) : p.in_hi;
+                        const uint32_t nb = ok ? 16u : 0u;
+                        cp_async16(d + (uint32_t)i * 2048u, src, nb);
+                        cp_async16(d + (uint32_t)i * 2048u + A_TILE_BYTES, ok ? src + p.in_plane : src, nb);
+                    }
+                    // the hardware arrives on the stage barrier once this thread's copies have landed:
+                    // no wait in the producer, up to STAGES chunks in flight
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+                } else {
+                    float vals[8][8];
+                    const int ci = te.x - ((int)(te.y == 31 ? 0 : te.y) / p.k * p.win + (int)(te.y == 31 ? 0 : te.y) % p.k) * p.pix_stride;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = (tmask[i] >> te.y) & 1u;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) vals[i][e] = 0.f;
+                        if (ok) {
+                            const size_t eo = (size_t)(pix_off[i] + te.x);
+                            if (MODE == TC_IN_F32) {
+                                const float4* src = reinterpret_cast<const float4*>(p.in_f32 + eo);
+                                float4 a = __ldg(src), b = __ldg(src + 1);
+                                vals[i][0] = a.x; vals[i][1] = a.y; vals[i][2] = a.z; vals[i][3] = a.w;
+                                vals[i][4] = b.x; vals[i][5] = b.y; vals[i][6] = b.z; vals[i][7] = b.w;
+                            } else {
+                                uint4 qh = __ldg(reinterpret_cast<const uint4*>(p.in_hi + eo));
+                                uint4 ql = __ldg(reinterpret_cast<const uint4*>(p.in_hi + p.in_plane + eo));
+                                float fh[8], fl[8];
+                                unpack8(qh, fh);
+                                unpack8(ql, fl);
+                                const float4* sp = reinterpret_cast<const float4*>(p.in_scale + (size_t)seg_idx[i] * p.cin + ci);
+                                float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vals[i][e] = (fh[e] + fl[e]) * sc[e];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint4 hi, lo;
+                        split8(vals[i], hi, lo);
+                        *reinterpret_cast<uint4*>(st + dst0 + i * 2048) = hi;
+                        *reinterpret_cast<uint4*>(st + dst0 + i * 2048 + A_TILE_BYTES) = lo;
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bar_full[s]);
+                }
+                if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+        if (MODE == TC_IN_PLANES) cp_async_wait_all();   // nothing may be in flight when the CTA exits
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(TM, NT);
+            uint32_t s = 0, ph = 0, it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const uint32_t a = it & 1u;
+                mbar_wait(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + a * (uint32_t)NT;
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&bar_full[s], ph);
+                    fence_proxy_async_smem();          // cp.async / st.shared (generic proxy) -> tcgen05 reads (async proxy)
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint64_t da_hi = umma_desc_sw128(a_hi);
+                    const uint64_t da_lo = umma_desc_sw128(a_hi + A_TILE_BYTES);
+                    const uint64_t db_hi = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES);
+                    const uint64_t db_lo = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES + (uint32_t)NT * 128u);
+                    int ksteps = (p.K - kc * KC + 15) >> 4;
+                    if (ksteps > 4) ksteps = 4;
+                    for (int j = 0; j < ksteps; ++j) {
+                        const uint64_t adv = (uint64_t)(kDescKStep * j);
+                        umma_f16(acc, da_hi + adv, db_hi + adv, idesc, (kc | j) != 0 ? 1u : 0u);
+                        umma_f16(acc, da_hi + adv, db_lo + adv, idesc, 1u);
+                        umma_f16(acc, da_lo + adv, db_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(&bar_empty[s]);        // frees the smem stage when these MMAs retire
+                    if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&bar_acc_full[a]);         // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        uint32_t it = 0;
+        const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int mt = p.n_tiles == 1 ? t : t / p.n_tiles;
+            const int n_tile = p.n_tiles == 1 ? 0 : t - mt * p.n_tiles;
+            const int m0 = mt * TM;
+            const uint32_t a = it & 1u;
+            mbar_wait(&bar_acc_full[a], (it >> 1) & 1u);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t t_lane = tmem_base + a * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
+            size_t spec_base = 0;
+            if (p.spec_nframes > 0 && row_ok) {
+                const int b = row / p.spec_nframes, tt = row - b * p.spec_nframes;
+                spec_base = ((size_t)b * p.cout * p.spec_nframes + tt) * p.spec_nch + p.spec_ch;
+            }
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                float v[16];
+                __syncwarp();                          // tcgen05.ld is .sync.aligned: reconverge first
+                tmem_ld16(t_lane + (uint32_t)c0, v);
+                const int n = n_tile * NT + c0;
+                if (!row_ok || n >= p.cout) continue;
+                if (p.spec_nframes > 0) {
+                    // spectrogram: square, power-compress, scatter (lanes = consecutive frames -> coalesced)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n + j >= p.cout) break;
+                        const float pw = v[j] * v[j];
+                        const float r = pw > 0.f ? exp2f(p.spec_exponent * __log2f(pw)) : pw;
+                        const size_t o = spec_base + (size_t)(n + j) * p.spec_nframes * p.spec_nch;
+                        const __half hh = __float2half_rn(r);
+                        p.out_hi[o] = hh;
+                        p.out_hi[p.out_plane + o] = __float2half_rn(r - __half2float(hh));
+                    }
+                    continue;
+                }
+                const size_t o = (size_t)row * p.cout + n;
+                if (vec) {
+                    const float* bs = s_bias_ok ? s_bias + n : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += bs ? bs[j] : __ldg(p.bias + n + j);
+                    if (p.act == KACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                    } else if (p.act == KACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+                    }
+                    if (p.res_hi) {
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + h8);
+                            uint4 rl = __ldg(reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + o) + h8);
+                            float fh[8], fl[8];
+                            unpack8(rh, fh);
+                            unpack8(rl, fl);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[8 * h8 + e] += fh[e] + fl[e];
+                        }
+                    }
+                    if (p.out_f32) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            reinterpret_cast<float4*>(p.out_f32 + o)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            uint4 hi, lo;
+                            split8(v + 8 * h8, hi, lo);
+                            reinterpret_cast<uint4*>(p.out_hi + o)[h8] = hi;
+                            reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o)[h8] = lo;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n + j >= p.cout) break;
+                        float r = act_fn(v[j] + p.bias[n + j], p.act);
+                        if (p.res_hi) r += __half2float(p.res_hi[o + j]) + __half2float(p.res_hi[p.res_plane + o + j]);
+                        if (p.out_f32) {
+                            p.out_f32[o + j] = r;
+                        } else {
+                            __half hh = __float2half_rn(r);
+                            p.out_hi[o + j] = hh;
+                            p.out_hi[p.out_plane + o + j] = __float2half_rn(r - __half2float(hh));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_empty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+size_t tc_conv_smem_bytes(int nt, int stages) {
+    return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)nt * 128) + 1024;
+}
+
+int tc_conv_pick_stages(int nt, int k_chunks) {
+    int s = MAX_STAGES;
+    while (s > 1 && tc_conv_smem_bytes(nt, s) > 200 * 1024) --s;
+    (void)k_chunks;                     // the ring runs across tiles, so depth is useful even for K <= 64
+    return s < 2 ? 2 : s;
+}
+
+cudaError_t tc_conv_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES_SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_tc_conv<TC_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+}
+
+cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stream) {
+    if (p.M <= 0) return cudaSuccess;
+    if (p.k_chunks > MAX_K_CHUNKS || p.k * p.k > 31) return cudaErrorInvalidValue;
+    if ((p.cin & 7) || p.nt < 16 || p.nt > 256 || (p.nt & 15) || p.stages < 2 || p.stages > MAX_STAGES ||
+        p.tmem_cols < 2 * p.nt || p.tmem_cols > 512)
+        return cudaErrorInvalidValue;
+    const int total = p.m_tiles * p.n_tiles;
+    dim3 grid((unsigned)(total < num_sms ? total : num_sms));
+    size_t smem = tc_conv_smem_bytes(p.nt, p.stages);
+    if (smem > 208 * 1024) return cudaErrorInvalidValue;
+    switch (p.in_mode) {
+        case TC_IN_PLANES: k_tc_conv<TC_IN_PLANES><<<grid, NTHREADS, smem, stream>>>(p); break;
+        case TC_IN_PLANES_SCALED: k_tc_conv<TC_IN_PLANES_SCALED><<<grid, NTHREADS, smem, stream>>>(p); break;
+        default: k_tc_conv<TC_IN_F32><<<grid, NTHREADS, smem, stream>>>(p); break;
+    }
+    return cudaGetLastError();
+}
+
+// Host: split + swizzle the [K][ldw] FP32 weight matrix into the per-(n_tile, k_chunk) smem images.
+void tc_pack_weights(const float* w, int K, int cout, int ldw, int nt, std::vector<uint16_t>& out,
+                     int* n_tiles_out, int* k_chunks_out) {
+    const int n_tiles = (cout + nt - 1) / nt;
+    const int k_chunks = (K + KC - 1) / KC;
+    const size_t img = (size_t)nt * 64;                        // halfs per plane image
+    out.assign((size_t)n_tiles * k_chunks * 2 * img, 0);
+    for (int t = 0; t < n_tiles; ++t)
+        for (int kc = 0; kc < k_chunks; ++kc) {
+            uint16_t* hi = out.data() + ((size_t)t * k_chunks + kc) * 2 * img;
+            uint16_t* lo = hi + img;
+            for (int nn = 0; nn < nt; ++nn) {
+                const int co = t * nt + nn;
+                if (co >= cout) continue;
+                for (int u = 0; u < 8; ++u)
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = kc * KC + u * 8 + e;
+                        if (k >= K) continue;
+                        const float x = w[(size_t)k * ldw + co];
+                        const __half h = __float2half_rn(x);
+                        const __half l = __float2half_rn(x - __half2float(h));
+                        const size_t idx = (sw128_offset((uint32_t)nn, (uint32_t)u) >> 1) + e;
+                        hi[idx] = *reinterpret_cast<const uint16_t*>(&h);
+                        lo[idx] = *reinterpret_cast<const uint16_t*>(&l);
+                    }
+            }
+        }
+    *n_tiles_out = n_tiles;
+    *k_chunks_out = k_chunks;
+}
+
+}  // namespace bn
