@@ -366,13 +366,62 @@ static inline PlanesPtr planes_of(bn_ctx* c, int t) {
 
 static void prof_mark(bn_ctx* c, const char* name);
 
+// squeeze-excite tail starting at op i?  (FC silu -> FC sigmoid -> conv gated by it, input = the
+// tensor whose pool feeds the first FC).  Returns the index of the gated conv or -1.
+static int match_se_tail(const Plan& p, size_t i) {
+    if (i + 2 >= p.ops.size()) return -1;
+    const PlanOp &f1 = p.ops[i], &f2 = p.ops[i + 1];
+    if (f1.kind != OP_LINEAR || f1.act != ACT_SILU || f2.kind != OP_LINEAR || f2.act != ACT_SIGMOID) return -1;
+    if (f2.in != f1.out || f1.in_scale >= 0 || f2.in_scale >= 0 || f1.residual >= 0 || f2.residual >= 0) return -1;
+    // the pooled vector must come from a GAP op
+    int gap = -1;
+    for (size_t j = 0; j < i; ++j)
+        if (p.ops[j].kind == OP_GAP && p.ops[j].out == f1.in) gap = (int)j;
+    if (gap < 0) return -1;
+    const int d = p.ops[gap].in;
+    for (size_t j = i + 2; j < p.ops.size() && j < i + 4; ++j) {
+        const PlanOp& cv = p.ops[j];
+        if (cv.in_scale == f2.out && cv.in == d && (cv.kind == OP_CONV)) {
+            // d may only be read by its pool and by this conv (it is rescaled in place)
+            for (size_t q = 0; q < p.ops.size(); ++q) {
+                if ((int)q == gap || q == j) continue;
+                if (p.ops[q].in == d || p.ops[q].residual == d) return -1;
+            }
+            for (auto& o : p.outputs) if (p.root(o.tensor) == p.root(d)) return -1;
+            return (int)j;
+        }
+    }
+    return -1;
+}
+
 static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
     bn_engine* e = c->eng;
     const Plan& p = e->plan;
     cudaStream_t s = c->stream;
+    int prescaled_conv = -1;                   // conv whose gated input was already rescaled in place
     for (size_t i = 0; i < p.ops.size(); ++i) {
         const PlanOp& op = p.ops[i];
         const DevOp& d = e->dev_ops[i];
+        if (op.kind == OP_LINEAR) {
+            const int cv = match_se_tail(p, i);
+            if (cv >= 0 && (p.tensors[p.ops[cv].in].C % 8) == 0) {
+                const PlanOp& f2 = p.ops[i + 1];
+                const TensorInfo& dt = p.tensors[p.ops[cv].in];
+                prof_mark(c, op.name.c_str());
+                SeParams sp{};
+                sp.pooled = c->d_tensor[op.in];
+                sp.w1 = d.weight; sp.b1 = d.bias; sp.ldw1 = op.ldw;
+                sp.w2 = e->dev_ops[i + 1].weight; sp.b2 = e->dev_ops[i + 1].bias; sp.ldw2 = f2.ldw;
+                sp.gate_out = c->d_tensor[f2.out];
+                sp.d = planes_of(c, p.ops[cv].in);
+                sp.c = dt.C; sp.r = op.cout; sp.npix = dt.H * dt.W;
+                BN_CUDA(launch_se_scale(sp, B, s));
+                ++launches;
+                prescaled_conv = cv;
+                ++i;                             // the second FC ran inside the fused kernel
+                continue;
+            }
+        }
         if (op.kind == OP_GAP) {
             // squeeze fused into the preceding depthwise conv?
             if (i > 0 && p.ops[i - 1].kind == OP_DWCONV && p.ops[i - 1].out == op.in) continue;
@@ -394,8 +443,9 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             if (in_sp) {
                 PlanesPtr ip = planes_of(c, op.in);
                 tp.in_hi = ip.hi; tp.in_plane = ip.plane;
-                tp.in_mode = op.in_scale >= 0 ? TC_IN_PLANES_SCALED : TC_IN_PLANES;
-                tp.in_scale = op.in_scale >= 0 ? c->d_tensor[op.in_scale] : nullptr;
+                const bool gated = op.in_scale >= 0 && (int)i != prescaled_conv;
+                tp.in_mode = gated ? TC_IN_PLANES_SCALED : TC_IN_PLANES;
+                tp.in_scale = gated ? c->d_tensor[op.in_scale] : nullptr;
             } else {
                 tp.in_f32 = c->d_tensor[op.in];
                 tp.in_mode = TC_IN_F32;
@@ -426,7 +476,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
         } else if (is_spatial(p, op.in) || is_spatial(p, op.out)) {
             ConvPlanesParams cp{};
             cp.in = planes_of(c, op.in);
-            cp.in_scale = op.in_scale >= 0 ? c->d_tensor[op.in_scale] : nullptr;
+            cp.in_scale = (op.in_scale >= 0 && (int)i != prescaled_conv) ? c->d_tensor[op.in_scale] : nullptr;
             cp.weight = d.weight; cp.bias = d.bias;
             if (op.residual >= 0) cp.residual = planes_of(c, op.residual);
             cp.out = planes_of(c, op.out);

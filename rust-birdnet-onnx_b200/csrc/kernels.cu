@@ -475,74 +475,72 @@ cudaError_t launch_spectrogram_v24_planes(const float* xnorm, const float* basis
 // thread then owns one channel and a strided set of output pixels.  The global average of the
 // activated output (the squeeze of squeeze-excite) is reduced in a fixed order -> deterministic.
 // ======================================================================================
-template <int CG>
+template <int K, int STRIDE, int CG>
 __global__ void __launch_bounds__(256) k_dwconv_planes(DwPlanesParams p) {
-    extern __shared__ __align__(16) float s_in[];          // [hin*win][CG]
+    extern __shared__ __align__(16) float s_in[];          // [(hin+2p)][(win+2p)][CG], zero halo
     __shared__ float s_part[256];
-    constexpr int PG = 256 / CG;                            // pixel groups
+    constexpr int PG = 256 / CG;                            // threads per channel
+    constexpr int XB = STRIDE == 1 ? 4 : 2;                 // outputs per thread along x
+    constexpr int NCOL = (XB - 1) * STRIDE + K;             // input columns one x-block touches
     const int cgroups = p.c / CG;
     const int b = blockIdx.x / cgroups, cg = blockIdx.x - b * cgroups;
     const int c0 = cg * CG;
-    const int npin = p.hin * p.win, npout = p.hout * p.wout;
-    const size_t in_base = (size_t)b * npin * p.c + c0;
-    // stage: CG/8 16-byte units per pixel and plane
-    constexpr int UPP = CG / 8;
-    for (int u = threadIdx.x; u < npin * UPP; u += 256) {
+    const int hp = p.hin + 2 * p.pad, wp = p.win + 2 * p.pad;
+    const int npout = p.hout * p.wout;
+    const size_t in_base = (size_t)b * p.hin * p.win * p.c + c0;
+    constexpr int UPP = CG / 8;                             // 16-byte units per pixel and plane
+    for (int u = threadIdx.x; u < hp * wp * UPP; u += 256) {
         const int pix = u / UPP, cu = u - pix * UPP;
-        const size_t o = in_base + (size_t)pix * p.c + cu * 8;
-        uint4 qh = __ldg(reinterpret_cast<const uint4*>(p.in.hi + o));
-        uint4 ql = __ldg(reinterpret_cast<const uint4*>(p.in.hi + p.in.plane + o));
-        const __half2* h = reinterpret_cast<const __half2*>(&qh);
-        const __half2* l = reinterpret_cast<const __half2*>(&ql);
+        const int y = pix / wp - p.pad, x = pix - (pix / wp) * wp - p.pad;
         float* dst = s_in + (size_t)pix * CG + cu * 8;
+        if (y >= 0 && y < p.hin && x >= 0 && x < p.win) {
+            const size_t o = in_base + ((size_t)y * p.win + x) * p.c + cu * 8;
+            uint4 qh = __ldg(reinterpret_cast<const uint4*>(p.in.hi + o));
+            uint4 ql = __ldg(reinterpret_cast<const uint4*>(p.in.hi + p.in.plane + o));
+            const __half2* h = reinterpret_cast<const __half2*>(&qh);
+            const __half2* l = reinterpret_cast<const __half2*>(&ql);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float2 a = __half22float2(h[i]), d = __half22float2(l[i]);
-            dst[2 * i] = a.x + d.x;
-            dst[2 * i + 1] = a.y + d.y;
+            for (int i = 0; i < 4; ++i) {
+                float2 a = __half22float2(h[i]), d = __half22float2(l[i]);
+                dst[2 * i] = a.x + d.x;
+                dst[2 * i + 1] = a.y + d.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = 0.f;
         }
     }
     const int cl = threadIdx.x % CG, pg = threadIdx.x / CG;
     const int c = c0 + cl;
-    float wreg[25];
-    const int k2 = p.k * p.k;
+    float wreg[K * K];
 #pragma unroll
-    for (int i = 0; i < 25; ++i) wreg[i] = i < k2 ? p.weight[(size_t)i * p.c + c] : 0.f;
+    for (int i = 0; i < K * K; ++i) wreg[i] = p.weight[(size_t)i * p.c + c];
     const float bias = p.bias[c];
     __syncthreads();
     float pool = 0.f;
-    for (int pix = pg; pix < npout; pix += PG) {
-        const int oy = pix / p.wout, ox = pix - oy * p.wout;
-        const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-        float acc = bias;
-        if (p.k == 3) {
+    const int xblocks = p.wout / XB;
+    for (int blk = pg; blk < p.hout * xblocks; blk += PG) {
+        const int oy = blk / xblocks, ox0 = (blk - oy * xblocks) * XB;
+        float acc[XB];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = iy0 + ky;
-                if (iy < 0 || iy >= p.hin) continue;
+        for (int j = 0; j < XB; ++j) acc[j] = bias;
+        const float* base = s_in + ((size_t)(oy * STRIDE) * wp + ox0 * STRIDE) * CG + cl;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = ix0 + kx;
-                    if (ix < 0 || ix >= p.win) continue;
-                    acc = fmaf(s_in[(size_t)(iy * p.win + ix) * CG + cl], wreg[ky * 3 + kx], acc);
-                }
-            }
-        } else {
+        for (int ky = 0; ky < K; ++ky) {
+            float col[NCOL];
 #pragma unroll
-            for (int ky = 0; ky < 5; ++ky) {
-                const int iy = iy0 + ky;
-                if (ky >= p.k || iy < 0 || iy >= p.hin) continue;
+            for (int x = 0; x < NCOL; ++x) col[x] = base[((size_t)ky * wp + x) * CG];
 #pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
-                    const int ix = ix0 + kx;
-                    if (kx >= p.k || ix < 0 || ix >= p.win) continue;
-                    acc = fmaf(s_in[(size_t)(iy * p.win + ix) * CG + cl], wreg[ky * p.k + kx], acc);
-                }
-            }
+            for (int j = 0; j < XB; ++j)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) acc[j] = fmaf(col[j * STRIDE + kx], wreg[ky * K + kx], acc[j]);
         }
-        acc = apply_act(acc, p.act);
-        split_store(p.out.hi, p.out.plane, ((size_t)b * npout + pix) * p.c + c, acc);
-        pool += acc;
+#pragma unroll
+        for (int j = 0; j < XB; ++j) {
+            const float v = apply_act(acc[j], p.act);
+            split_store(p.out.hi, p.out.plane, ((size_t)b * npout + oy * p.wout + ox0 + j) * p.c + c, v);
+            pool += v;
+        }
     }
     if (p.pooled) {
         s_part[threadIdx.x] = pool;
@@ -556,19 +554,117 @@ __global__ void __launch_bounds__(256) k_dwconv_planes(DwPlanesParams p) {
     }
 }
 
+template <int K, int STRIDE>
+static cudaError_t launch_dw_ks(const DwPlanesParams& p, int cg, size_t smem, cudaStream_t stream) {
+    const int grid = p.batch * (p.c / cg);
+    if (cg == 64) k_dwconv_planes<K, STRIDE, 64><<<grid, 256, smem, stream>>>(p);
+    else if (cg == 32) k_dwconv_planes<K, STRIDE, 32><<<grid, 256, smem, stream>>>(p);
+    else k_dwconv_planes<K, STRIDE, 16><<<grid, 256, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int K, int STRIDE>
+static void dw_set_attr() {
+    cudaFuncSetAttribute(k_dwconv_planes<K, STRIDE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dwconv_planes<K, STRIDE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dwconv_planes<K, STRIDE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 cudaError_t launch_dwconv_planes(const DwPlanesParams& p, cudaStream_t stream) {
     if (p.batch <= 0) return cudaSuccess;
-    if (p.k * p.k > 25 || (p.c & 15)) return cudaErrorInvalidValue;
-    const int npin = p.hin * p.win;
-    // largest channel group whose FP32 patch fits in ~96 KB of shared memory
+    if ((p.k != 3 && p.k != 5) || (p.stride != 1 && p.stride != 2) || (p.c & 15) || p.pad != p.k / 2) return cudaErrorInvalidValue;
+    const int xb = p.stride == 1 ? 4 : 2;
+    if (p.wout % xb) return cudaErrorInvalidValue;
+    const size_t np = (size_t)(p.hin + 2 * p.pad) * (p.win + 2 * p.pad);
+    // largest channel group whose zero-padded FP32 patch fits in ~100 KB (two CTAs per SM)
     int cg = 64;
-    while (cg > 16 && ((p.c % cg) != 0 || (size_t)npin * cg * 4 > 96 * 1024)) cg >>= 1;
-    if ((p.c % cg) != 0 || (size_t)npin * cg * 4 > 200 * 1024) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)npin * cg * 4;
-    const int grid = p.batch * (p.c / cg);
-    if (cg == 64) k_dwconv_planes<64><<<grid, 256, smem, stream>>>(p);
-    else if (cg == 32) k_dwconv_planes<32><<<grid, 256, smem, stream>>>(p);
-    else k_dwconv_planes<16><<<grid, 256, smem, stream>>>(p);
+    while (cg > 16 && ((p.c % cg) != 0 || np * cg * 4 > 100 * 1024)) cg >>= 1;
+    if ((p.c % cg) != 0 || np * cg * 4 > 200 * 1024) return cudaErrorInvalidValue;
+    const size_t smem = np * cg * 4;
+    if (p.k == 3 && p.stride == 1) return launch_dw_ks<3, 1>(p, cg, smem, stream);
+    if (p.k == 3) return launch_dw_ks<3, 2>(p, cg, smem, stream);
+    if (p.stride == 1) return launch_dw_ks<5, 1>(p, cg, smem, stream);
+    return launch_dw_ks<5, 2>(p, cg, smem, stream);
+}
+
+// ======================================================================================
+// Squeeze-excite tail, one kernel: r = silu(W1^T p + b1); s = sigmoid(W2^T r + b2); then the
+// depthwise output is rescaled IN PLACE (d <- d * s) so the projection conv can stream it with
+// cp.async like any other tensor.  grid = (chunks, B); every CTA recomputes the two tiny FCs.
+// ======================================================================================
+__global__ void __launch_bounds__(256) k_se_scale(SeParams p) {
+    extern __shared__ float s_se[];                 // pooled[C] | gate[C] | r[R] | partial[8][R]
+    float* s_p = s_se;
+    float* s_g = s_se + p.c;
+    float* s_r = s_g + p.c;
+    float* s_part = s_r + p.r;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < p.c; i += 256) s_p[i] = p.pooled[(size_t)b * p.c + i];
+    __syncthreads();
+    // FC1: warps split the C range, lanes = output j (coalesced rows of W1[c][ldw1])
+    const int cpw = (p.c + 7) / 8;
+    const int cbeg = warp * cpw, cend = min(p.c, cbeg + cpw);
+    for (int j0 = 0; j0 < p.r; j0 += 32) {
+        const int j = j0 + lane;
+        float acc = 0.f;
+        if (j < p.r) {
+            for (int cc = cbeg; cc < cend; ++cc) acc = fmaf(s_p[cc], p.w1[(size_t)cc * p.ldw1 + j], acc);
+            s_part[warp * p.r + j] = acc;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < p.r; j += 256) {
+        float v = p.b1[j];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_part[w * p.r + j];
+        s_r[j] = v * (1.0f / (1.0f + expf(-v)));
+    }
+    __syncthreads();
+    // FC2: thread per channel, W2[j][ldw2] rows are contiguous in c
+    for (int cc = tid; cc < p.c; cc += 256) {
+        float v = p.b2[cc];
+        for (int j = 0; j < p.r; ++j) v = fmaf(s_r[j], p.w2[(size_t)j * p.ldw2 + cc], v);
+        const float g = 1.0f / (1.0f + expf(-v));
+        s_g[cc] = g;
+        if (p.gate_out && blockIdx.x == 0) p.gate_out[(size_t)b * p.c + cc] = g;
+    }
+    __syncthreads();
+    // rescale this CTA's share of the pixels, 8 channels (16 bytes per plane) per thread-step
+    const int upp = p.c >> 3;
+    const int total_u = p.npix * upp;
+    const int per = (total_u + gridDim.x - 1) / gridDim.x;
+    const int ubeg = blockIdx.x * per, uend = min(total_u, ubeg + per);
+    __half* base = p.d.hi + (size_t)b * p.npix * p.c;
+    for (int u = ubeg + tid; u < uend; u += 256) {
+        const int cu = (u % upp) << 3;
+        __half* ph = base + (size_t)u * 8;
+        uint4 qh = *reinterpret_cast<const uint4*>(ph);
+        uint4 ql = *reinterpret_cast<const uint4*>(ph + p.d.plane);
+        const __half2* h = reinterpret_cast<const __half2*>(&qh);
+        const __half2* l = reinterpret_cast<const __half2*>(&ql);
+        __half2 oh[4], ol[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 a = __half22float2(h[i]), d = __half22float2(l[i]);
+            const float v0 = (a.x + d.x) * s_g[cu + 2 * i], v1 = (a.y + d.y) * s_g[cu + 2 * i + 1];
+            oh[i] = __floats2half2_rn(v0, v1);
+            float2 bk = __half22float2(oh[i]);
+            ol[i] = __floats2half2_rn(v0 - bk.x, v1 - bk.y);
+        }
+        *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<uint4*>(oh);
+        *reinterpret_cast<uint4*>(ph + p.d.plane) = *reinterpret_cast<uint4*>(ol);
+    }
+}
+
+cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    if ((p.c & 7) || p.r > 256) return cudaErrorInvalidValue;
+    const size_t smem = ((size_t)2 * p.c + p.r + 8 * p.r) * sizeof(float);
+    int chunks = (p.npix * (p.c >> 3) + 4095) / 4096;      // ~16 units per thread
+    if (chunks < 1) chunks = 1;
+    if (chunks > 16) chunks = 16;
+    dim3 grid(chunks, batch);
+    k_se_scale<<<grid, 256, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -870,9 +966,7 @@ static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 constexpr int kMaxSortSmem = 220 * 1024;
 
 cudaError_t init_kernels_for_device() {
-    cudaFuncSetAttribute(k_dwconv_planes<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_dwconv_planes<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_dwconv_planes<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    dw_set_attr<3, 1>(); dw_set_attr<3, 2>(); dw_set_attr<5, 1>(); dw_set_attr<5, 2>();
     cudaError_t e = cudaFuncSetAttribute(k_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSortSmem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_range_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSortSmem);

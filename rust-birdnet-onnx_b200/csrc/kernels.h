@@ -92,6 +92,18 @@ struct DwPlanesParams {
 };
 cudaError_t launch_dwconv_planes(const DwPlanesParams& p, cudaStream_t stream);
 cudaError_t launch_gap_planes(PlanesPtr in, float* out, int batch, int hw, int c, cudaStream_t stream);
+// fused squeeze-excite tail: two FCs on the pooled vector + in-place rescale of the planes tensor d
+struct SeParams {
+    const float* pooled;   // [B][c]
+    const float* w1;       // [c][ldw1]  (r outputs)
+    const float* b1;       // [r]
+    const float* w2;       // [r][ldw2]  (c outputs)
+    const float* b2;       // [c]
+    float* gate_out;       // [B][c] or nullptr
+    PlanesPtr d;           // [B][npix][c], rescaled in place
+    int c, r, ldw1, ldw2, npix;
+};
+cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream);
 
 // ---- epilogue (rows A4 / A6) ------------------------------------------------------
 struct TopkParams {

@@ -50,7 +50,7 @@ __device__ __forceinline__ void unpack8(const uint4& q, float v[8]) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) k_tc_conv(TcConvParams p) {
+__global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_conv(TcConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_conv(TcConvParams p) {
         const int rbase = tid >> 3;
         const int hw = p.hout * p.wout;
         const uint32_t dst0 = sw128_offset((uint32_t)rbase, (uint32_t)unit);   // row i: + i*2048
+        const __half* in_lo = p.in_hi + p.in_plane;
         uint32_t s = 0, ph = 0;                // ring slot / phase of the chunk being issued
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int m0 = (t / p.n_tiles) * TM;
@@ -127,11 +128,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_conv(TcConvParams p) {
                 for (int i = 0; i < 8; ++i) {
                     if (m + 16 * i < p.M) {
                         const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-                        uint32_t xm = 0, mk = 0;
-                        for (int kx = 0; kx < p.k; ++kx) xm |= (uint32_t)(ix0 + kx >= 0 && ix0 + kx < p.win) << kx;
-                        for (int ky = 0; ky < p.k; ++ky)
-                            if (iy0 + ky >= 0 && iy0 + ky < p.hin) mk |= xm << (ky * p.k);
-                        tmask[i] = mk;
+                        // taps kx in [xl, xh) and ky in [yl, yh) fall inside the image
+                        const int xl = max(0, -ix0), xh = min(p.k, p.win - ix0);
+                        const int yl = max(0, -iy0), yh = min(p.k, p.hin - iy0);
+                        const uint32_t xm = xh > xl ? ((1u << xh) - 1u) & ~((1u << xl) - 1u) : 0u;
+                        uint32_t yrep = 0;             // sum of 1 << (ky*k) over valid ky (k <= 5)
+#pragma unroll
+                        for (int ky = 0; ky < 5; ++ky)
+                            if (ky >= yl && ky < yh) yrep |= 1u << (ky * p.k);
+                        tmask[i] = xm * yrep;          // xm < 2^k: the shifted copies do not overlap
                         pix_off[i] = b * p.seg_stride + (iy0 * p.win + ix0) * p.pix_stride;
                         seg_idx[i] = (uint32_t)b;
                     } else {
@@ -158,10 +163,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_conv(TcConvParams p) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const bool ok = (tmask[i] >> te.y) & 1u;
-                        const __half* src = ok ? p.in_hi + (pix_off[i] + te.x) : p.in_hi;
+                        const int eo = ok ? pix_off[i] + te.x : 0;      // clamp: masked taps never form an address
                         const uint32_t nb = ok ? 16u : 0u;
-                        cp_async16(d + (uint32_t)i * 2048u, src, nb);
-                        cp_async16(d + (uint32_t)i * 2048u + A_TILE_BYTES, ok ? src + p.in_plane : src, nb);
+                        cp_async16(d + (uint32_t)i * 2048u, p.in_hi + eo, nb);
+                        cp_async16(d + (uint32_t)i * 2048u + A_TILE_BYTES, in_lo + eo, nb);
                     }
                     // the hardware arrives on the stage barrier once this thread's copies have landed:
                     // no wait in the producer, up to STAGES chunks in flight
@@ -351,10 +356,14 @@ size_t tc_conv_smem_bytes(int nt, int stages) {
 }
 
 int tc_conv_pick_stages(int nt, int k_chunks) {
-    int s = MAX_STAGES;
-    while (s > 1 && tc_conv_smem_bytes(nt, s) > 200 * 1024) --s;
     (void)k_chunks;                     // the ring runs across tiles, so depth is useful even for K <= 64
-    return s < 2 ? 2 : s;
+    // prefer two CTAs per SM (<= 104 KB each) when at least two stages fit, else one deep ring
+    int s = MAX_STAGES;
+    while (s > 2 && tc_conv_smem_bytes(nt, s) > 104 * 1024) --s;
+    if (tc_conv_smem_bytes(nt, s) <= 104 * 1024) return s;
+    s = MAX_STAGES;
+    while (s > 2 && tc_conv_smem_bytes(nt, s) > 200 * 1024) --s;
+    return s;
 }
 
 cudaError_t tc_conv_init_device() {
@@ -372,8 +381,11 @@ cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stre
         p.tmem_cols < 2 * p.nt || p.tmem_cols > 512)
         return cudaErrorInvalidValue;
     const int total = p.m_tiles * p.n_tiles;
-    dim3 grid((unsigned)(total < num_sms ? total : num_sms));
     size_t smem = tc_conv_smem_bytes(p.nt, p.stages);
+    // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
+    const int per_sm = (p.in_mode == TC_IN_PLANES && smem <= 104 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    const int slots = num_sms * per_sm;
+    dim3 grid((unsigned)(total < slots ? total : slots));
     if (smem > 208 * 1024) return cudaErrorInvalidValue;
     switch (p.in_mode) {
         case TC_IN_PLANES: k_tc_conv<TC_IN_PLANES><<<grid, NTHREADS, smem, stream>>>(p); break;

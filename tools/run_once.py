@@ -15,3 +15,22 @@ ctx = clf.create_batch_context(B)
 for _ in range(reps):
     out = ctx.run_device(d.data_ptr(), B, True)
 print("ok", out.batch, ctx.last_launch_count())
+if os.environ.get("PROFILE"):
+    import collections
+    ctx.set_profiling(True)
+    acc = collections.OrderedDict()
+    for _ in range(5):
+        ctx.run_device(d.data_ptr(), B, True)
+        for n, ms in ctx.stage_times():
+            acc.setdefault(n, []).append(ms)
+    tot = 0
+    for n, v in acc.items():
+        m = sum(v) / len(v); tot += m
+        print(f"{n:28s} {m:8.4f}")
+    print("TOTAL", tot)
+    import time
+    ctx.set_profiling(False)
+    t = time.time()
+    for _ in range(20): ctx.enqueue_device(d.data_ptr(), B, True)
+    ctx.wait(); dt = (time.time() - t) / 20
+    print(f"back-to-back: {dt*1e3:.3f} ms/batch -> {B/dt:.0f} seg/s")
