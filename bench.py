@@ -189,16 +189,21 @@ def _stage_roofline(spec, stage_times, batch, peaks):
         if "_" in base and base.rsplit("_", 1)[1].isdigit() and base.rsplit("_", 1)[0] in rows:
             base = base.rsplit("_", 1)[0]
         d = {"stage": name, "ms": ms, "share": ms / total}
-        if base in rows and rows[base]["kind"] in ("conv", "gemm"):
+        if base in rows:
+            # a layer is bound by whichever is slower at peak: its FLOPs on the tensor pipe or its
+            # activation + weight bytes through HBM (FP32-equivalent storage: 4 B per element)
             r = rows[base]
             flops = 2.0 * r["macs"] * batch
-            d.update(bound="tensor", achieved=flops / (ms * 1e-3) / 1e12, peak=peaks["tf_sust"], unit="TFLOP/s",
-                     alg_per_segment=2 * r["macs"])
-        elif base in rows:                                      # depthwise: bandwidth-bound
-            r = rows[base]
-            byts = 4.0 * (r["in_elems"] + r["out_elems"] + r["w_elems"] / batch) * batch
-            d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
-                     alg_per_segment=4 * (r["in_elems"] + r["out_elems"]))
+            byts = 4.0 * ((r["in_elems"] + r["out_elems"]) * batch + r["w_elems"])
+            t_tensor = flops / (peaks["tf_sust"] * 1e12)
+            t_hbm = byts / (peaks["hbm"] * 1e9)
+            if r["kind"] != "dw" and t_tensor >= t_hbm:
+                d.update(bound="tensor", achieved=flops / (ms * 1e-3) / 1e12, peak=peaks["tf_sust"], unit="TFLOP/s",
+                         alg_per_segment=2 * r["macs"])
+            else:
+                d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                         alg_per_segment=4 * (r["in_elems"] + r["out_elems"]),
+                         tensor_tflops=flops / (ms * 1e-3) / 1e12)
         elif name.startswith("spectrogram"):
             s = fe.specs[int(name[-1])]
             t = s.n_frames(fe.sample_count)
@@ -370,7 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--pipeline-depth", type=int, default=2)
+    ap.add_argument("--pipeline-depth", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

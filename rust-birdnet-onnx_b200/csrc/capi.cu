@@ -205,6 +205,7 @@ int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_e
 int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems) {
     if (!ctx || !dst) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
     if (!ctx->d_norm) return set_error(BN_ERR_INVALID_ARGUMENT, "model has no normaliser");
+    if (!ctx->keep_normalized) return set_error(BN_ERR_INVALID_ARGUMENT, "normalised audio is not kept: set BN_KEEP_NORMALIZED=1 before creating the context");
     uint64_t n = std::min<uint64_t>(dst_elems, ctx->max_batch * (uint64_t)ctx->eng->plan.sample_count);
     BN_CUDA(cudaSetDevice(ctx->eng->device));
     BN_CUDA(cudaStreamSynchronize(ctx->stream));

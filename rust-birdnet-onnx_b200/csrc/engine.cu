@@ -273,6 +273,7 @@ bn_ctx::~bn_ctx() {
     if (h_in) cudaFreeHost(h_in);
     if (d_in) cudaFree(d_in);
     if (d_norm) cudaFree(d_norm);
+    if (d_minmax) cudaFree(d_minmax);
     for (auto* x : d_xp) if (x) cudaFree(x);
     for (size_t i = 0; i < d_tensor.size(); ++i)
         if (d_tensor[i] && eng->plan.tensors[i].alias_of < 0 && eng->plan.tensors[i].scale_base < 0) cudaFree(d_tensor[i]);
@@ -307,6 +308,8 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     memset(c->h_in, 0, mb * S * sizeof(float));    // vec![0.0f32; max*sample_count], batch_context.rs:122
     BN_CUDA(cudaMalloc(&c->d_in, mb * S * sizeof(float)));
     if (p.fe.normalize) BN_CUDA(cudaMalloc(&c->d_norm, mb * S * sizeof(float)));
+    BN_CUDA(cudaMalloc(&c->d_minmax, mb * 2 * sizeof(uint32_t)));
+    { const char* kn = getenv("BN_KEEP_NORMALIZED"); c->keep_normalized = !e->tc_mode || (kn && kn[0] == '1'); }
     for (auto& ft : e->fe_tc) {
         __half* x = nullptr;
         BN_CUDA(cudaMalloc(&x, 2 * mb * (size_t)ft.rows * ft.row_stride * sizeof(__half)));
@@ -513,9 +516,9 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
             const auto& ft = e->fe_tc[bi];
             outs[bi] = FePlaneOut{c->d_xp[bi], mb * (size_t)ft.rows * ft.row_stride, ft.hop, ft.row_stride, ft.rows};
         }
-        BN_CUDA(launch_minmax_normalize_fe(d_audio, c->d_norm, outs, (int)e->fe_tc.size(), B, p.sample_count,
-                                           p.fe.eps, p.fe.half, p.fe.two, s));
-        ++launches;
+        BN_CUDA(launch_minmax_normalize_fe(d_audio, c->keep_normalized ? c->d_norm : nullptr, c->d_minmax, outs,
+                                           (int)e->fe_tc.size(), B, p.sample_count, p.fe.eps, p.fe.half, p.fe.two, s));
+        launches += 3;
         fe_in = c->d_norm;
     } else if (p.fe.normalize) {
         BN_CUDA(launch_minmax_normalize(d_audio, c->d_norm, B, p.sample_count, p.fe.eps, p.fe.half, p.fe.two, s));

@@ -87,6 +87,8 @@ struct bn_ctx {
     float* h_in = nullptr;       // pinned [max_batch][S]
     float* d_in = nullptr;       // [max_batch][S]
     float* d_norm = nullptr;     // [max_batch][S] normalised audio (v2.4 front-end)
+    uint32_t* d_minmax = nullptr;   // [max_batch][2] order-preserving keys of the per-segment min / max
+    bool keep_normalized = true;   // write the FP32 normalised audio (tests: BN_KEEP_NORMALIZED=1; always in FP32 mode)
     std::vector<__half*> d_xp;   // per branch: hi/lo planes of the frame matrix [max_batch][rows][row_stride]
     std::vector<float*> d_tensor;   // per plan tensor (aliases resolved to their root)
     float* h_logits = nullptr;   // pinned

@@ -150,14 +150,125 @@ __global__ void __launch_bounds__(1024) k_minmax_normalize_fe(const float* __res
     }
 }
 
-cudaError_t launch_minmax_normalize_fe(const float* x, float* y, const FePlaneOut* outs, int n_outs, int batch,
-                                       int sample_count, float eps, float half, float two, cudaStream_t stream) {
+// ---- two-kernel form: (1) per-segment min / max over SLICES CTAs with order-preserving integer
+// atomics (min / max are order independent -> deterministic), (2) normalise + emit, SLICES CTAs
+// per segment.  Keeps all 148 SMs busy for B = 256 (a 1-CTA-per-segment kernel runs 1.7 waves).
+constexpr int NORM_SLICES = 8;
+
+__device__ __forceinline__ uint32_t f2key(float x) {
+    uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) k_minmax_init(uint32_t* mm, int batch) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < batch) { mm[2 * i] = 0xFFFFFFFFu; mm[2 * i + 1] = 0u; }
+}
+
+__global__ void __launch_bounds__(512) k_minmax_partial(const float* __restrict__ x, uint32_t* __restrict__ mm, int S) {
+    const int b = blockIdx.y;
+    const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)b * S);
+    const int n4 = S >> 2;
+    const int per = (n4 + gridDim.x - 1) / gridDim.x;
+    const int beg = blockIdx.x * per, end = min(n4, beg + per);
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        float4 v = x4[i];
+        mn = nan_min(nan_min(mn, v.x), nan_min(nan_min(v.y, v.z), v.w));
+        mx = nan_max(nan_max(mx, v.x), nan_max(nan_max(v.y, v.z), v.w));
+    }
+    if (blockIdx.x == gridDim.x - 1)
+        for (int i = (n4 << 2) + threadIdx.x; i < S; i += blockDim.x) {
+            const float v = x[(size_t)b * S + i];
+            mn = nan_min(mn, v);
+            mx = nan_max(mx, v);
+        }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // nan_min / nan_max propagate NaN, so a NaN anywhere in the slice shows up here
+        if (mn != mn || mx != mx) {
+            atomicMax(mm + 2 * b + 1, 0xFFC00000u);   // canonical +NaN key: poisons the segment
+        } else {
+            atomicMin(mm + 2 * b, f2key(mn));
+            atomicMax(mm + 2 * b + 1, f2key(mx));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) k_normalize_emit(const float* __restrict__ x, float* __restrict__ y, const uint32_t* __restrict__ mm,
+                                                        FeOuts fo, int S, float eps, float half, float two) {
+    const int b = blockIdx.y;
+    const float* xs = x + (size_t)b * S;
+    float lo = key2f(mm[2 * b]);
+    float hi_v = key2f(mm[2 * b + 1]);
+    if (hi_v != hi_v) lo = hi_v;                       // any NaN poisons the whole segment, like torch
+    const float den = __fadd_rn(__fsub_rn(hi_v, lo), eps);
+    if (y) {
+        float* ys = y + (size_t)b * S;
+        const int n4 = S >> 2;
+        const int per = (n4 + gridDim.x - 1) / gridDim.x;
+        const int beg = blockIdx.x * per, end = min(n4, beg + per);
+        const float4* x4 = reinterpret_cast<const float4*>(xs);
+        float4* y4 = reinterpret_cast<float4*>(ys);
+        for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+            float4 v = x4[i], r;
+            r.x = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.x, lo), den), half), two);
+            r.y = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.y, lo), den), half), two);
+            r.z = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.z, lo), den), half), two);
+            r.w = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(v.w, lo), den), half), two);
+            y4[i] = r;
+        }
+        if (blockIdx.x == gridDim.x - 1)
+            for (int i = (n4 << 2) + threadIdx.x; i < S; i += blockDim.x)
+                ys[i] = __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(xs[i], lo), den), half), two);
+    }
+    for (int bi = 0; bi < fo.n; ++bi) {
+        const FePlaneOut o = fo.o[bi];
+        const int units_per_row = o.row_stride >> 3;
+        const int n_units = o.rows * units_per_row;
+        const int per = (n_units + gridDim.x - 1) / gridDim.x;
+        const int beg = blockIdx.x * per, end = min(n_units, beg + per);
+        __half* hi = o.hi + (size_t)b * o.rows * o.row_stride;
+        for (int u = beg + threadIdx.x; u < end; u += blockDim.x) {
+            const int r = u / units_per_row, c0 = (u - r * units_per_row) << 3;
+            __half2 h[4], l[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                float v[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + 2 * e2 + q;
+                    const int src = r * o.hop + c;
+                    v[q] = (c < o.hop && src < S)
+                               ? __fmul_rn(__fsub_rn(__fdiv_rn(__fsub_rn(xs[src], lo), den), half), two) : 0.f;
+                }
+                h[e2] = __floats2half2_rn(v[0], v[1]);
+                float2 bk = __half22float2(h[e2]);
+                l[e2] = __floats2half2_rn(v[0] - bk.x, v[1] - bk.y);
+            }
+            *reinterpret_cast<uint4*>(hi + (size_t)u * 8) = *reinterpret_cast<uint4*>(h);
+            *reinterpret_cast<uint4*>(hi + o.plane + (size_t)u * 8) = *reinterpret_cast<uint4*>(l);
+        }
+    }
+}
+
+cudaError_t launch_minmax_normalize_fe(const float* x, float* y, uint32_t* minmax_scratch, const FePlaneOut* outs, int n_outs,
+                                       int batch, int sample_count, float eps, float half, float two, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     if (n_outs > 2) return cudaErrorInvalidValue;
     FeOuts fo{};
     fo.n = n_outs;
     for (int i = 0; i < n_outs; ++i) fo.o[i] = outs[i];
-    k_minmax_normalize_fe<<<batch, 1024, 0, stream>>>(x, y, fo, sample_count, eps, half, two);
+    k_minmax_init<<<(batch + 255) / 256, 256, 0, stream>>>(minmax_scratch, batch);
+    dim3 grid(NORM_SLICES, batch);
+    k_minmax_partial<<<grid, 512, 0, stream>>>(x, minmax_scratch, sample_count);
+    k_normalize_emit<<<grid, 512, 0, stream>>>(x, y, minmax_scratch, fo, sample_count, eps, half, two);
     return cudaGetLastError();
 }
 
@@ -672,61 +783,101 @@ cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream) {
 // Stem: direct k x k conv for tiny Cin (the 2-channel spectrogram), planes in / planes out.
 // One thread per output pixel computes all Cout (<= 32) channels; weights live in smem.
 // ======================================================================================
-__global__ void __launch_bounds__(128) k_stem_planes(ConvPlanesParams p, int K) {
-    extern __shared__ float s_w[];                          // [K][cout] then bias[cout]
-    for (int i = threadIdx.x; i < K * p.cout; i += blockDim.x) s_w[i] = p.weight[(size_t)(i / p.cout) * p.ldw + (i % p.cout)];
-    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_w[K * p.cout + i] = p.bias[i];
-    __syncthreads();
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long M = (long long)p.batch * p.hout * p.wout;
-    if (m >= M) return;
-    const int hw = p.hout * p.wout;
-    const int b = (int)(m / hw), rem = (int)(m - (long long)b * hw);
-    const int oy = rem / p.wout, ox = rem - oy * p.wout;
-    float acc[32];
+// CTA = one strip of STRIP output pixels of one output row; the k input rows it needs are staged
+// in smem as FP32; thread = (pixel slot, channel quad) with its k*k*cin x 4 weights in registers.
+template <int K, int CIN, int STRIDE>
+__global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
+    constexpr int STRIP = 128;
+    constexpr int WIN = (STRIP - 1) * STRIDE + K;               // input columns per strip
+    __shared__ float s_x[K][WIN * CIN];
+    const int quads = p.cout >> 2;                               // 8 for cout = 32
+    const int slots = 256 / quads;                               // pixel slots per pass
+    const int strips = (p.wout + STRIP - 1) / STRIP;
+    const int q = threadIdx.x % quads, slot = threadIdx.x / quads;
+    float w[K * K * CIN][4];
 #pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = n < p.cout ? s_w[K * p.cout + n] : 0.f;
-    const size_t in_base = (size_t)b * p.hin * p.win * p.cin;
-    for (int ky = 0; ky < p.k; ++ky) {
-        const int iy = oy * p.stride - p.pad + ky;
-        if (iy < 0 || iy >= p.hin) continue;
-        for (int kx = 0; kx < p.k; ++kx) {
-            const int ix = ox * p.stride - p.pad + kx;
-            if (ix < 0 || ix >= p.win) continue;
-            const size_t o = in_base + ((size_t)iy * p.win + ix) * p.cin;
-            for (int ci = 0; ci < p.cin; ++ci) {
-                const float x = planes_load(p.in.hi, p.in.plane, o + ci);
-                const float* w = s_w + (size_t)((ky * p.k + kx) * p.cin + ci) * p.cout;
+    for (int t = 0; t < K * K * CIN; ++t) {
+        const float4 wv = *reinterpret_cast<const float4*>(p.weight + (size_t)t * p.ldw + q * 4);
+        w[t][0] = wv.x; w[t][1] = wv.y; w[t][2] = wv.z; w[t][3] = wv.w;
+    }
+    const float4 bv = *reinterpret_cast<const float4*>(p.bias + q * 4);
+    const int total = p.batch * p.hout * strips;
+    for (int work = blockIdx.x; work < total; work += gridDim.x) {     // persistent: weights stay in registers
+    const int strip = work % strips;
+    const int oy = (work / strips) % p.hout;
+    const int b = work / (strips * p.hout);
+    const int ox0 = strip * STRIP;
+    const int ix_base = ox0 * STRIDE - p.pad, iy_base = oy * STRIDE - p.pad;
+    const size_t in_base = (size_t)b * p.hin * p.win * CIN;
+    __syncthreads();                                                   // previous strip fully consumed
+    // stage K rows x WIN pixels: one 4-byte (2-channel) load per pixel and plane, all loads of a
+    // thread issued before any shared-memory store so their latencies overlap
+    static_assert(CIN == 2, "pixel = one 32-bit word per plane");
+    constexpr int NPIX = K * WIN;
+    constexpr int NLD = (NPIX + 255) / 256;
+    uint32_t vh[NLD], vl[NLD];
+    const uint32_t* ph32 = reinterpret_cast<const uint32_t*>(p.in.hi);
+    const uint32_t* pl32 = reinterpret_cast<const uint32_t*>(p.in.hi + p.in.plane);
 #pragma unroll
-                for (int n = 0; n < 32; ++n)
-                    if (n < p.cout) acc[n] = fmaf(x, w[n], acc[n]);
-            }
+    for (int j = 0; j < NLD; ++j) {
+        const int i = threadIdx.x + j * 256;
+        const int ky = i / WIN, x = i - ky * WIN;
+        const int iy = iy_base + ky, ix = ix_base + x;
+        vh[j] = 0u; vl[j] = 0u;
+        if (i < NPIX && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
+            const size_t o = (in_base >> 1) + (size_t)iy * p.win + ix;
+            vh[j] = __ldg(ph32 + o);
+            vl[j] = __ldg(pl32 + o);
         }
     }
-    const size_t oo = (size_t)m * p.cout;
 #pragma unroll
-    for (int n8 = 0; n8 < 4; ++n8) {
-        if (n8 * 8 >= p.cout) break;
-        __half2 h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float a = apply_act(acc[n8 * 8 + 2 * i], p.act), d = apply_act(acc[n8 * 8 + 2 * i + 1], p.act);
-            h[i] = __floats2half2_rn(a, d);
-            float2 bk = __half22float2(h[i]);
-            l[i] = __floats2half2_rn(a - bk.x, d - bk.y);
+    for (int j = 0; j < NLD; ++j) {
+        const int i = threadIdx.x + j * 256;
+        if (i < NPIX) {
+            const int ky = i / WIN, x = i - ky * WIN;
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vh[j]));
+            const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&vl[j]));
+            s_x[ky][x * 2] = a.x + d.x;
+            s_x[ky][x * 2 + 1] = a.y + d.y;
         }
-        *reinterpret_cast<uint4*>(p.out.hi + oo + n8 * 8) = *reinterpret_cast<uint4*>(h);
-        *reinterpret_cast<uint4*>(p.out.hi + p.out.plane + oo + n8 * 8) = *reinterpret_cast<uint4*>(l);
+    }
+    __syncthreads();
+    for (int px = slot; px < STRIP && ox0 + px < p.wout; px += slots) {
+        float acc[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float x = s_x[ky][(px * STRIDE + kx) * CIN + ci];
+                    const int t = (ky * K + kx) * CIN + ci;
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) acc[n] = fmaf(x, w[t][n], acc[n]);
+                }
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[n] = apply_act(acc[n], p.act);
+        const __half2 h0 = __floats2half2_rn(acc[0], acc[1]), h1 = __floats2half2_rn(acc[2], acc[3]);
+        const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(acc[0] - b0.x, acc[1] - b0.y), l1 = __floats2half2_rn(acc[2] - b1.x, acc[3] - b1.y);
+        const size_t o = (((size_t)b * p.hout + oy) * p.wout + ox0 + px) * p.cout + q * 4;
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(p.out.hi + o) = hv;
+        *reinterpret_cast<uint2*>(p.out.hi + p.out.plane + o) = lv;
+    }
     }
 }
 
 cudaError_t launch_stem_planes(const ConvPlanesParams& p, cudaStream_t stream) {
-    const long long M = (long long)p.batch * p.hout * p.wout;
-    if (M <= 0) return cudaSuccess;
-    if (p.cout > 32 || (p.cout & 7) || p.in_scale || p.residual.hi) return cudaErrorInvalidValue;
-    const int K = p.k * p.k * p.cin;
-    const size_t smem = ((size_t)K * p.cout + p.cout) * sizeof(float);
-    k_stem_planes<<<(unsigned)((M + 127) / 128), 128, smem, stream>>>(p, K);
+    if (p.batch <= 0) return cudaSuccess;
+    if (p.k != 3 || p.cin != 2 || p.stride != 2 || (p.cout & 3) || p.cout > 64 || (256 % (p.cout >> 2)) || p.in_scale || p.residual.hi)
+        return cudaErrorInvalidValue;
+    const int strips = (p.wout + 127) / 128;
+    const long long total = (long long)p.batch * p.hout * strips;
+    const int grid = (int)(total < 148 * 6 ? total : 148 * 6);
+    k_stem_planes<3, 2, 2><<<grid, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -961,6 +1112,75 @@ __global__ void __launch_bounds__(1024) k_topk(TopkParams p, int P) {
 __global__ void k_range_filter(const Pred* in, const uint32_t* in_count, int stride, const uint8_t* state,
                                const float* score, int n, int rerank, Pred* out, uint32_t* out_count, int P);
 
+// Small-k path (k <= 32): k rounds of block-wide arg-max over register-resident keys instead of a
+// full sort.  Keys are (total-order(logit) << 32 | ~index), so every key is unique and the order
+// is the documented one (higher logit first, lower index first on ties).
+constexpr int TOPK_SMALL_EPT = 32;
+__global__ void __launch_bounds__(1024) k_topk_small(TopkParams p) {
+    __shared__ unsigned long long s_wmax[32];
+    __shared__ unsigned long long s_best;
+    __shared__ unsigned long long s_keys[64];
+    __shared__ uint32_t s_idx[32];
+    __shared__ float s_conf[32];
+    __shared__ int s_warp[33];
+    __shared__ int s_cnt;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const float* lg = p.logits + (size_t)b * p.n;
+    unsigned long long keys[TOPK_SMALL_EPT];
+#pragma unroll
+    for (int j = 0; j < TOPK_SMALL_EPT; ++j) {
+        const int i = tid + j * blockDim.x;
+        keys[j] = i < p.n ? (((unsigned long long)total_order_key(lg[i]) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+    }
+    for (uint32_t r = 0; r < p.k; ++r) {
+        unsigned long long m = 0ull;
+#pragma unroll
+        for (int j = 0; j < TOPK_SMALL_EPT; ++j) m = keys[j] > m ? keys[j] : m;
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t > m ? t : m;
+        }
+        if (lane == 0) s_wmax[warp] = m;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long t = lane < nw ? s_wmax[lane] : 0ull;
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long u = __shfl_xor_sync(0xffffffffu, t, o);
+                t = u > t ? u : t;
+            }
+            if (lane == 0) { s_best = t; s_keys[r] = t; }
+        }
+        __syncthreads();
+        const unsigned long long best = s_best;
+#pragma unroll
+        for (int j = 0; j < TOPK_SMALL_EPT; ++j)
+            if (keys[j] == best) keys[j] = 0ull;
+    }
+    // sigmoid + min_confidence on the k survivors (one warp; order is already confidence-descending)
+    if (warp == 0) {
+        uint32_t idx = 0;
+        float conf = 0.f;
+        int keep = 0;
+        if (lane < (int)p.k) {
+            const unsigned long long kk = s_keys[lane];
+            idx = 0xFFFFFFFFu - (uint32_t)(kk & 0xFFFFFFFFull);
+            const float x = from_total_order_key((uint32_t)(kk >> 32));
+            conf = 1.0f / (1.0f + expf(-x));
+            keep = (!p.has_min_conf) || (conf >= p.min_conf);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = __popc(bal & ((1u << lane) - 1u));
+            s_idx[pos] = idx;
+            s_conf[pos] = conf;
+        }
+        if (lane == 0) s_cnt = __popc(bal);
+    }
+    __syncthreads();
+    filter_and_emit(s_idx, s_conf, s_keys, s_cnt, p.range_state, p.range_score, p.n, p.rerank,
+                    p.out + (size_t)b * p.k, p.out_count + b, s_warp);
+}
+
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 constexpr int kMaxSortSmem = 220 * 1024;
@@ -974,6 +1194,12 @@ cudaError_t init_kernels_for_device() {
 
 cudaError_t launch_topk(const TopkParams& p, cudaStream_t stream) {
     if (p.batch <= 0) return cudaSuccess;
+    if (p.k >= 1 && p.k <= 32 && p.n <= TOPK_SMALL_EPT * 1024) {
+        int threads = ((p.n + TOPK_SMALL_EPT - 1) / TOPK_SMALL_EPT + 31) / 32 * 32;
+        if (threads < 64) threads = 64;
+        k_topk_small<<<p.batch, threads, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     const int P = next_pow2(p.n < 2 ? 2 : p.n);
     size_t smem = (size_t)P * 8 + (size_t)p.k * 8;
     if (smem > (size_t)kMaxSortSmem) return cudaErrorInvalidValue;

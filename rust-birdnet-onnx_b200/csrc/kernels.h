@@ -64,8 +64,9 @@ struct FePlaneOut {
     size_t plane;       // lo = hi + plane
     int hop, row_stride, rows;
 };
-cudaError_t launch_minmax_normalize_fe(const float* x, float* y, const FePlaneOut* outs, int n_outs, int batch,
-                                       int sample_count, float eps, float half, float two, cudaStream_t stream);
+// y may be nullptr (normalised FP32 audio is only kept for tests); minmax_scratch: [batch][2] u32
+cudaError_t launch_minmax_normalize_fe(const float* x, float* y, uint32_t* minmax_scratch, const FePlaneOut* outs, int n_outs,
+                                       int batch, int sample_count, float eps, float half, float two, cudaStream_t stream);
 // framed DFT x mel -> square -> pow, written as planes
 cudaError_t launch_spectrogram_v24_planes(const float* xnorm, const float* basis, int ldb, PlanesPtr spec,
                                           int batch, int sample_count, int n_fft, int hop, int n_frames,

@@ -172,7 +172,9 @@ def test_stages_against_oracle(clf, oracle):
     import torch
     B = 10                                               # one segment of every synthetic kind
     audio = synth.batch(0, B, 144000, 48000)
+    os.environ["BN_KEEP_NORMALIZED"] = "1"               # keep the FP32 normalised audio for this context
     ctx = clf.create_batch_context(B)
+    del os.environ["BN_KEEP_NORMALIZED"]
     res = clf.predict_batch_with_context(ctx, list(audio))
     ref = oracle.forward(audio, keep=["spec"])
     norm_ref = oracle.frontend(torch.from_numpy(audio))["normalized"].numpy()

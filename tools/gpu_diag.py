@@ -18,6 +18,7 @@ clf = bb.Classifier.builder().model_path(path).labels(synthetic_labels(spec.num_
 print("build s", time.time() - t0, "nproc", os.cpu_count())
 B = 10
 audio = synth.batch(0, B, 144000, 48000)
+os.environ["BN_KEEP_NORMALIZED"] = "1"
 ctx = clf.create_batch_context(B)
 res = clf.predict_batch_with_context(ctx, list(audio))
 orc = ModelOracle(spec, load_initializers(path))
