@@ -107,6 +107,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Generic K-major swizzled tile: rows of `row_bytes` = 32 / 64 / 128 (SWIZZLE_32B / 64B / 128B: layout
+// type 6 / 4 / 2), 8-row atoms, SBO = 8 * row_bytes.  Tile base aligned to 8 * row_bytes.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((row_bytes * 8u) >> 4) << 32) |
+           (1ull << 46) | (layout << 61);
+}
+// 5-D tiled TMA load global -> shared, completion (bytes) on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 // advancing K by 16 fp16 (32 bytes) inside the swizzle atom = +2 in the start-address field
 constexpr uint32_t kDescKStep = 2;
 

@@ -50,7 +50,8 @@ __device__ __forceinline__ void unpack8(const uint4& q, float v[8]) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_conv(TcConvParams p) {
+__global__ void __launch_bounds__(NTHREADS, (MODE == TC_IN_PLANES || MODE == TC_IN_TMA) ? 2 : 1)
+k_tc_conv(const __grid_constant__ TcConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_c
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bar_full[s], 129);      // 128 producer threads + thread 0's expect_tx arrive
+            // cp.async modes: 128 producer threads + thread 0's expect_tx arrive; TMA: thread 0 only
+            mbar_init(&bar_full[s], MODE == TC_IN_TMA ? 1 : 129);
             mbar_init(&bar_empty[s], 1);       // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -102,7 +104,50 @@ __global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_c
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
 
-    if (warp < 4) {
+    if (MODE == TC_IN_TMA && warp < 4) {
+        // ================================ TMA producer (one thread) ================================
+        if (tid == 0) {
+            tma_prefetch_desc(&p.tmap);
+            const uint32_t sub_bytes = (uint32_t)TM * (uint32_t)p.kb * 2u;       // one [128][kb] fp16 box
+            const int subs_per_chunk = KC / p.kb;
+            uint32_t s = 0, ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int mt = t / p.n_tiles, n_tile = t - mt * p.n_tiles;
+                const int b = mt / p.tiles_per_seg, lt = mt - b * p.tiles_per_seg;
+                int x0, y0, seg;
+                if (p.flat) {
+                    x0 = p.tiles_per_seg == p.m_tiles ? mt * TM : lt * TM;     // flat matrix row / frame index
+                    y0 = 0;
+                    seg = p.tiles_per_seg == p.m_tiles ? 0 : b;
+                } else {
+                    const int lp0 = lt * TM;
+                    const int oy0 = lp0 / p.wout, ox0 = lp0 - oy0 * p.wout;
+                    x0 = ox0 * p.stride - p.pad;
+                    y0 = oy0 * p.stride - p.pad;
+                    seg = b;
+                }
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    mbar_wait(&bar_empty[s], ph ^ 1u);
+                    uint8_t* st = tiles + (size_t)s * stage_bytes;
+                    int nsub = (p.K - kc * KC + p.kb - 1) / p.kb;
+                    if (nsub > subs_per_chunk) nsub = subs_per_chunk;
+                    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
+                                 ::"r"(smem_u32(&bar_full[s])), "r"(w_bytes + 2u * (uint32_t)nsub * sub_bytes) : "memory");
+                    for (int sb = 0; sb < nsub; ++sb) {
+                        const int k0 = kc * KC + sb * p.kb;
+                        const int tap = k0 / p.tab_cin, ci = k0 - tap * p.tab_cin;
+                        const int ky = tap / p.k, kx = tap - ky * p.k;
+                        tma_load_5d(st + (size_t)sb * sub_bytes, &p.tmap, ci, x0 + kx, y0 + ky, seg, 0, &bar_full[s]);
+                        tma_load_5d(st + A_TILE_BYTES + (size_t)sb * sub_bytes, &p.tmap, ci, x0 + kx, y0 + ky, seg, 1, &bar_full[s]);
+                    }
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)n_tile * p.k_chunks + kc) * w_bytes;
+                    bulk_copy_g2s(st + 2 * A_TILE_BYTES, src, w_bytes, &bar_full[s]);
+                    if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 4) {
         // ================================ A / W producers ================================
         // Per thread: one 16-byte K unit (8 channels) of 8 rows (rbase + 16*i).  Everything that
         // does not depend on the K chunk is hoisted to tile setup: per row a 32-bit element offset
@@ -218,6 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_c
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(TM, NT);
+            const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const uint32_t a = it & 1u;
@@ -229,17 +275,21 @@ __global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_c
                     fence_proxy_async_smem();          // cp.async / st.shared (generic proxy) -> tcgen05 reads (async proxy)
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t da_hi = umma_desc_sw128(a_hi);
-                    const uint64_t da_lo = umma_desc_sw128(a_hi + A_TILE_BYTES);
                     const uint64_t db_hi = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES);
                     const uint64_t db_lo = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES + (uint32_t)NT * 128u);
                     int ksteps = (p.K - kc * KC + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
                     for (int j = 0; j < ksteps; ++j) {
+                        // A: K block of kb channels per sub-tile (kb = 64 -> one SWIZZLE_128B tile per chunk)
+                        const uint32_t kk = (uint32_t)j * 16u;
+                        const uint32_t sub = kk / a_kb, in_sub = kk - sub * a_kb;
+                        const uint32_t a_off = sub * (uint32_t)TM * a_kb * 2u;
+                        const uint64_t da_hi = umma_desc_kmajor(a_hi + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
+                        const uint64_t da_lo = umma_desc_kmajor(a_hi + A_TILE_BYTES + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
                         const uint64_t adv = (uint64_t)(kDescKStep * j);
-                        umma_f16(acc, da_hi + adv, db_hi + adv, idesc, (kc | j) != 0 ? 1u : 0u);
-                        umma_f16(acc, da_hi + adv, db_lo + adv, idesc, 1u);
-                        umma_f16(acc, da_lo + adv, db_hi + adv, idesc, 1u);
+                        umma_f16(acc, da_hi, db_hi + adv, idesc, (kc | j) != 0 ? 1u : 0u);
+                        umma_f16(acc, da_hi, db_lo + adv, idesc, 1u);
+                        umma_f16(acc, da_lo, db_hi + adv, idesc, 1u);
                     }
                     umma_commit(&bar_empty[s]);        // frees the smem stage when these MMAs retire
                     if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
@@ -256,12 +306,13 @@ __global__ void __launch_bounds__(NTHREADS, MODE == TC_IN_PLANES ? 2 : 1) k_tc_c
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int mt = p.n_tiles == 1 ? t : t / p.n_tiles;
             const int n_tile = p.n_tiles == 1 ? 0 : t - mt * p.n_tiles;
-            const int m0 = mt * TM;
+            const int sb = mt / p.tiles_per_seg, lt = mt - sb * p.tiles_per_seg;
+            const int lp = lt * TM + q * 32 + lane;            // row inside the segment
             const uint32_t a = it & 1u;
             mbar_wait(&bar_acc_full[a], (it >> 1) & 1u);
             tc_fence_after();
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row = sb * p.pix_per_seg + lp;
+            const bool row_ok = lp < p.pix_per_seg && row < p.M;
             const uint32_t t_lane = tmem_base + a * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
             size_t spec_base = 0;
             if (p.spec_nframes > 0 && row_ok) {
@@ -371,11 +422,18 @@ cudaError_t tc_conv_init_device() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES_SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_tc_conv<TC_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
 }
 
-cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stream) {
-    if (p.M <= 0) return cudaSuccess;
+cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t stream) {
+    if (pin.M <= 0) return cudaSuccess;
+    TcConvParams p = pin;
+    if (p.in_mode != TC_IN_TMA || p.tiles_per_seg <= 0) {      // cp.async modes: one flat "segment"
+        if (p.in_mode != TC_IN_TMA) { p.tiles_per_seg = p.m_tiles; p.pix_per_seg = p.M; }
+    }
+    if (p.in_mode == TC_IN_TMA && (p.kb != 16 && p.kb != 32 && p.kb != 64)) return cudaErrorInvalidValue;
     if (p.k_chunks > MAX_K_CHUNKS || p.k * p.k > 31) return cudaErrorInvalidValue;
     if ((p.cin & 7) || p.nt < 16 || p.nt > 256 || (p.nt & 15) || p.stages < 2 || p.stages > MAX_STAGES ||
         p.tmem_cols < 2 * p.nt || p.tmem_cols > 512)
@@ -383,16 +441,39 @@ cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stre
     const int total = p.m_tiles * p.n_tiles;
     size_t smem = tc_conv_smem_bytes(p.nt, p.stages);
     // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
-    const int per_sm = (p.in_mode == TC_IN_PLANES && smem <= 104 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    const int per_sm = ((p.in_mode == TC_IN_PLANES || p.in_mode == TC_IN_TMA) && smem <= 104 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
     const int slots = num_sms * per_sm;
     dim3 grid((unsigned)(total < slots ? total : slots));
     if (smem > 208 * 1024) return cudaErrorInvalidValue;
     switch (p.in_mode) {
         case TC_IN_PLANES: k_tc_conv<TC_IN_PLANES><<<grid, NTHREADS, smem, stream>>>(p); break;
         case TC_IN_PLANES_SCALED: k_tc_conv<TC_IN_PLANES_SCALED><<<grid, NTHREADS, smem, stream>>>(p); break;
+        case TC_IN_TMA: k_tc_conv<TC_IN_TMA><<<grid, NTHREADS, smem, stream>>>(p); break;
         default: k_tc_conv<TC_IN_F32><<<grid, NTHREADS, smem, stream>>>(p); break;
     }
     return cudaGetLastError();
+}
+
+bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                    const uint32_t box[5], const uint32_t elem_strides[5], int kb) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) != cudaSuccess || !sym) return false;
+        fn = reinterpret_cast<EncodeFn>(sym);
+    }
+    const CUtensorMapSwizzle sw = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < 5; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides[i]; }
+    for (int i = 0; i < 4; ++i) gs[i] = strides_bytes[i];
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 // Host: split + swizzle the [K][ldw] FP32 weight matrix into the per-(n_tile, k_chunk) smem images.

@@ -5,6 +5,7 @@
 // same 4 bytes per element as FP32).  The split is done ONCE by the producing kernel's epilogue,
 // so the tensor-core consumers can move operands with cp.async and no ALU work.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -14,9 +15,18 @@
 
 namespace bn {
 
-enum TcInMode : int { TC_IN_PLANES = 0, TC_IN_PLANES_SCALED = 1, TC_IN_F32 = 2 };
+enum TcInMode : int { TC_IN_PLANES = 0, TC_IN_PLANES_SCALED = 1, TC_IN_F32 = 2, TC_IN_TMA = 3 };
 
 struct TcConvParams {
+    // TC_IN_TMA: 5-D tensor map (channel, x, y, segment, plane) over the input hi/lo planes; the A
+    // tile of a K block is ONE cp.async.bulk.tensor per plane (zero fill outside the image = padding)
+    alignas(64) CUtensorMap tmap;
+    int kb;                  // channels per TMA box: 16 / 32 / 64 <-> SWIZZLE_32B / 64B / 128B
+    int box_w, box_h;        // output pixels per tile row x rows per tile (box_w * box_h == 128), rect mode
+    int flat;                // 1: A is a flat [M][K] matrix (1x1 stride-1 conv, front-end frames)
+    // tile -> rows: m tile mt covers rows [lt*128, lt*128+128) of segment b = mt / tiles_per_seg
+    // (cp.async modes: tiles_per_seg = m_tiles, pix_per_seg = M, i.e. one flat "segment")
+    int tiles_per_seg, pix_per_seg;
     // input: planes (lo = in_hi + in_plane) or FP32
     const __half* in_hi;
     size_t in_plane;
@@ -49,6 +59,9 @@ cudaError_t tc_conv_init_device();
 cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stream);
 size_t tc_conv_smem_bytes(int nt, int stages);
 int tc_conv_pick_stages(int nt, int k_chunks);
+// Encodes the 5-D (channel, x, y, segment, plane) fp16 tensor map; returns false if the driver refuses.
+bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                    const uint32_t box[5], const uint32_t elem_strides[5], int kb);
 void tc_pack_weights(const float* w, int K, int cout, int ldw, int nt, std::vector<uint16_t>& out,
                      int* n_tiles_out, int* k_chunks_out);
 
