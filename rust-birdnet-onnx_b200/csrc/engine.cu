@@ -194,6 +194,16 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             DevOp& d = e->dev_ops[i];
             const int K = op.k * op.k * op.cin;
             d.nt = choose_nt(op.cout);
+            // 3x3 stride-1 layers on wide images: halo mode if some N tile lets the weights stay resident
+            const char* env_halo = getenv("BN_DISABLE_HALO");
+            if (!(env_halo && env_halo[0] == '1') && op.kind == OP_CONV && op.in_scale < 0) {
+                const int c16 = (op.cout + 15) / 16 * 16;
+                for (int nt = d.nt; nt >= 16; nt -= 16) {
+                    if (c16 % nt) continue;
+                    const int slots = tc_conv_halo_slots(op.k, op.stride, op.pad, op.cin, op.wout, op.win, nt, (K + 63) / 64);
+                    if (slots >= 2) { d.nt = nt; d.halo_slots = slots; break; }
+                }
+            }
             std::vector<uint16_t> pack;
             tc_pack_weights(op.weight.data(), K, op.cout, op.ldw, d.nt, pack, &d.n_tiles, &d.k_chunks);
             d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks);
@@ -246,7 +256,40 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             }
         }
     } else {
-        return set_error(BN_ERR_MODEL_LOAD, "log-mel front-end is not implemented in this engine build yet");
+        if (!tc_enabled) return set_error(BN_ERR_MODEL_LOAD, "the log-mel front-end needs the tensor-core (planes) path; unset BN_DISABLE_TC");
+        const SpecBranch& br = p.fe.branches[0];
+        auto& lm = e->fe_lm;
+        if (br.n_bins != br.n_fft / 2 + 1) return set_error(BN_ERR_MODEL_LOAD, "log-mel front-end: mel matrix rows != n_fft/2 + 1");
+        if (!logmel_factorize(br.n_fft, lm.radix, &lm.n_stages) || logmel_smem_bytes(br.n_fft) > 96 * 1024)
+            return set_error(BN_ERR_MODEL_LOAD, "log-mel front-end: unsupported STFT length " + std::to_string(br.n_fft));
+        BN_CUDA(logmel_init_device());
+        std::vector<float> tw;
+        logmel_twiddles(br.n_fft, tw);
+        // banded form of the mel matrix: filter m = bins [lo, lo + cnt) (zeros inside the band are kept)
+        std::vector<int> lo(br.n_mels, 0), cnt(br.n_mels, 0), off(br.n_mels, 0);
+        std::vector<float> wv;
+        for (int m = 0; m < br.n_mels; ++m) {
+            int first = -1, last = -1;
+            for (int f = 0; f < br.n_bins; ++f)
+                if (br.mel[(size_t)f * br.n_mels + m] != 0.f) { if (first < 0) first = f; last = f; }
+            off[m] = (int)wv.size();
+            if (first >= 0) {
+                lo[m] = first; cnt[m] = last - first + 1;
+                for (int f = first; f <= last; ++f) wv.push_back(br.mel[(size_t)f * br.n_mels + m]);
+            }
+        }
+        if (wv.empty()) wv.push_back(0.f);
+        auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+            cudaError_t ce = cudaMalloc(dst, bytes);
+            if (ce != cudaSuccess) return ce;
+            return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        };
+        BN_CUDA(up(br.window.data(), br.window.size() * sizeof(float), (void**)&lm.window));
+        BN_CUDA(up(tw.data(), tw.size() * sizeof(float), (void**)&lm.twiddle));
+        BN_CUDA(up(lo.data(), lo.size() * sizeof(int), (void**)&lm.mel_lo));
+        BN_CUDA(up(cnt.data(), cnt.size() * sizeof(int), (void**)&lm.mel_cnt));
+        BN_CUDA(up(off.data(), off.size() * sizeof(int), (void**)&lm.mel_off));
+        BN_CUDA(up(wv.data(), wv.size() * sizeof(float), (void**)&lm.mel_w));
     }
     *out = e.release();
     return BN_OK;
@@ -264,6 +307,12 @@ bn_engine::~bn_engine() {
     }
     for (auto* b : d_basis) cudaFree(b);
     for (auto& f : fe_tc) if (f.wpack) cudaFree(f.wpack);
+    if (fe_lm.window) cudaFree(fe_lm.window);
+    if (fe_lm.twiddle) cudaFree(fe_lm.twiddle);
+    if (fe_lm.mel_lo) cudaFree(fe_lm.mel_lo);
+    if (fe_lm.mel_cnt) cudaFree(fe_lm.mel_cnt);
+    if (fe_lm.mel_off) cudaFree(fe_lm.mel_off);
+    if (fe_lm.mel_w) cudaFree(fe_lm.mel_w);
 }
 
 bn_ctx::~bn_ctx() {
@@ -447,7 +496,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
                 PlanesPtr ip = planes_of(c, op.in);
                 tp.in_hi = ip.hi; tp.in_plane = ip.plane;
                 const bool gated = op.in_scale >= 0 && (int)i != prescaled_conv;
-                tp.in_mode = gated ? TC_IN_PLANES_SCALED : TC_IN_PLANES;
+                tp.in_mode = gated ? TC_IN_PLANES_SCALED : (d.halo_slots > 0 ? TC_IN_HALO : TC_IN_PLANES);
                 tp.in_scale = gated ? c->d_tensor[op.in_scale] : nullptr;
             } else {
                 tp.in_f32 = c->d_tensor[op.in];
@@ -474,7 +523,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             tp.M = B * op.hout * op.wout;
             tp.pix_stride = op.cin; tp.seg_stride = op.hin * op.win * op.cin; tp.tab_cin = op.cin;
             tp.k_chunks = d.k_chunks; tp.n_tiles = d.n_tiles; tp.m_tiles = (tp.M + 127) / 128;
-            tp.nt = d.nt; tp.stages = d.stages; tp.tmem_cols = d.tmem_cols;
+            tp.nt = d.nt; tp.stages = tp.in_mode == TC_IN_HALO ? d.halo_slots : d.stages; tp.tmem_cols = d.tmem_cols;
             BN_CUDA(launch_tc_conv(tp, e->num_sms, s));
         } else if (is_spatial(p, op.in) || is_spatial(p, op.out)) {
             ConvPlanesParams cp{};
@@ -485,7 +534,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             cp.out = planes_of(c, op.out);
             cp.batch = B; cp.hin = op.hin; cp.win = op.win; cp.cin = op.cin; cp.hout = op.hout; cp.wout = op.wout;
             cp.cout = op.cout; cp.ldw = op.ldw; cp.k = op.k; cp.stride = op.stride; cp.pad = op.pad; cp.act = op.act;
-            if (op.cout <= 32 && (op.cout & 7) == 0 && op.in_scale < 0 && op.residual < 0 && op.cin <= 4)
+            if (op.cout <= 32 && (op.cout & 7) == 0 && op.in_scale < 0 && op.residual < 0 && (op.cin == 1 || op.cin == 2) && op.k == 3 && op.stride == 2)
                 BN_CUDA(launch_stem_planes(cp, s));
             else
                 BN_CUDA(launch_conv_igemm_planes(cp, s));
@@ -507,7 +556,7 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     cudaStream_t s = c->stream;
     uint64_t launches = 0;
     const float* fe_in = d_audio;
-    prof_mark(c, "normalize");
+    if (p.fe.kind != FE_LOGMEL) prof_mark(c, "normalize");
     const bool fe_on_tc = e->tc_mode && !e->fe_tc.empty() && p.fe.normalize;
     if (fe_on_tc) {
         const size_t mb = std::max<uint64_t>(c->max_batch, 1);
@@ -526,6 +575,23 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
         fe_in = c->d_norm;
     }
     float* spec = c->d_tensor[p.fe.out_tensor];
+    if (p.fe.kind == FE_LOGMEL) {
+        const SpecBranch& br = p.fe.branches[0];
+        const auto& lm = e->fe_lm;
+        prof_mark(c, "logmel");
+        LogmelParams lp{};
+        lp.audio = d_audio; lp.batch = B; lp.sample_count = p.sample_count;
+        lp.window = lm.window; lp.twiddle = reinterpret_cast<const float2*>(lm.twiddle);
+        lp.mel_lo = lm.mel_lo; lp.mel_cnt = lm.mel_cnt; lp.mel_off = lm.mel_off; lp.mel_w = lm.mel_w;
+        lp.n_fft = br.n_fft; lp.hop = br.hop; lp.n_frames = br.n_frames; lp.n_mels = br.n_mels;
+        for (int i = 0; i < 8; ++i) lp.radix[i] = lm.radix[i];
+        lp.n_stages = lm.n_stages;
+        lp.log_floor = p.fe.log_floor; lp.log_scale = p.fe.log_scale;
+        lp.out = planes_of(c, p.fe.out_tensor);
+        lp.out_f32 = nullptr;
+        BN_CUDA(launch_logmel(lp, s));
+        ++launches;
+    } else
     for (size_t bi = 0; bi < p.fe.branches.size(); ++bi) {
         const SpecBranch& br = p.fe.branches[bi];
         prof_mark(c, bi == 0 ? "spectrogram0" : "spectrogram1");

@@ -38,6 +38,7 @@ struct DevOp {
     bool use_tc = false;
     void* wpack = nullptr;
     int nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32;
+    int halo_slots = 0;          // > 0: TC_IN_HALO (patch staged once, taps as shifted views)
 };
 
 struct RangeDev {   // dense per-class tri-state on the device
@@ -71,6 +72,11 @@ struct bn_engine {
     // tensor-core front-end: per branch the block-Toeplitz frame matrix geometry + packed basis
     struct FeTc { void* wpack = nullptr; int hop = 0, row_stride = 0, rows = 0, K = 0, nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32; };
     std::vector<FeTc> fe_tc;
+    // log-mel front-end (32 kHz graphs): window, float64-built twiddles, banded mel filters
+    struct FeLogmel {
+        float* window = nullptr; float* twiddle = nullptr; int* mel_lo = nullptr; int* mel_cnt = nullptr; int* mel_off = nullptr;
+        float* mel_w = nullptr; int radix[8] = {0}; int n_stages = 0;
+    } fe_lm;
     std::mutex post_mu;
     bn::PostCfg post;
     std::mutex ctx_mu;

@@ -1,0 +1,194 @@
+// Log-mel front-end of the 32 kHz graphs (BirdNET v3.0, Perch v2):
+//
+//   frames (Hann window, no centre padding, zero pad_end) -> |STFT| -> mel matrix -> log_scale * ln(. + log_floor)
+//
+// The magnitude sits between the DFT and the mel projection, so unlike the v2.4 front-end this is
+// not one linear map and does not belong on the tensor cores: a 1024-point real FFT is ~25 kFLOP
+// where the DFT-as-GEMM would be 2 MFLOP.  One CTA transforms FRAMES_PER_PASS frames at a time in
+// shared memory:
+//   * real FFT of length N as a complex Stockham FFT of length M = N/2 over z[n] = x[2n] + i x[2n+1]
+//     (mixed radix 2/3/4/5, twiddles from a float64-built table staged in smem),
+//   * split:  X[k] = E[k] + W_N^k O[k],  E = (Z[k] + conj Z[M-k])/2,  O = -i (Z[k] - conj Z[M-k])/2,
+//   * |X[k]| for k = 0..N/2, then the mel projection as a banded sum (each triangular filter is a
+//     contiguous run of bins), log, hi/lo fp16 split, 256-byte coalesced row stores.
+// HBM: audio read once (overlapping frames hit L1/L2), spectrogram written once.
+#include "kernels.h"
+
+#include <cmath>
+#include <vector>
+
+namespace bn {
+
+namespace {
+
+constexpr int LM_THREADS = 256;
+constexpr int LM_FRAMES = 4;        // frames transformed concurrently by one CTA
+constexpr int LM_PASSES = 2;        // passes per CTA (twiddle table staged once)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// One Stockham stage of radix R over F interleaved transforms of length M.
+//   x[j + r*M/R] * W^(r * (j % Ns))  -> R-point DFT ->  y[(j / Ns) * Ns * R + j % Ns + r * Ns]
+// tw[m] = exp(-2*pi*i*m / (2M)); W_(Ns*R)^q = tw[q * (2M / (Ns*R))].
+template <int R>
+__device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, float2* __restrict__ y,
+                                               const float2* __restrict__ tw, int M, int Ns, int F) {
+    const int nb = M / R;
+    const int tstep = (2 * M) / (Ns * R);
+    for (int w = threadIdx.x; w < nb * F; w += LM_THREADS) {
+        const int f = w / nb, j = w - f * nb;
+        const float2* xf = x + f * M;
+        float2* yf = y + f * M;
+        const int k = j % Ns;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = xf[j + r * nb];
+            if (r > 0 && Ns > 1) v[r] = cmul(v[r], tw[r * k * tstep]);
+        }
+        float2 o[R];
+        if (R == 2) {
+            o[0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
+            o[1] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+        } else if (R == 4) {
+            const float2 a = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
+            const float2 b = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+            const float2 c = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
+            const float2 d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+            o[0] = make_float2(a.x + c.x, a.y + c.y);
+            o[2] = make_float2(a.x - c.x, a.y - c.y);
+            o[1] = make_float2(b.x + d.y, b.y - d.x);      // b - i d
+            o[3] = make_float2(b.x - d.y, b.y + d.x);      // b + i d
+        } else {
+            // generic small DFT (R = 3, 5): o[q] = sum_p v[p] * W_R^(p q)
+            const int rstep = (2 * M) / R;
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                float2 s = v[0];
+#pragma unroll
+                for (int p = 1; p < R; ++p) {
+                    const float2 t = cmul(v[p], tw[((p * q) % R) * rstep]);
+                    s.x += t.x; s.y += t.y;
+                }
+                o[q] = s;
+            }
+        }
+        const int d0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) yf[d0 + r * Ns] = o[r];
+    }
+}
+
+__global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
+    extern __shared__ __align__(16) unsigned char lm_smem[];
+    const int N = p.n_fft, M = N >> 1;
+    float2* tw = reinterpret_cast<float2*>(lm_smem);             // [N]
+    float2* buf0 = tw + N;                                       // [LM_FRAMES][M]
+    float2* buf1 = buf0 + LM_FRAMES * M;                         // [LM_FRAMES][M]
+    for (int i = threadIdx.x; i < N; i += LM_THREADS) tw[i] = p.twiddle[i];
+    const int b = blockIdx.y;
+    const float* xs = p.audio + (size_t)b * p.sample_count;
+    const int bins = M + 1;
+    for (int pass = 0; pass < LM_PASSES; ++pass) {
+        const int t0 = (blockIdx.x * LM_PASSES + pass) * LM_FRAMES;
+        if (t0 >= p.n_frames) break;                             // uniform across the CTA
+        const int F = min(LM_FRAMES, p.n_frames - t0);
+        __syncthreads();                                         // twiddles staged / previous pass consumed
+        // windowed frames, even samples -> re, odd samples -> im; zero beyond the segment (pad_end)
+        for (int w = threadIdx.x; w < F * M; w += LM_THREADS) {
+            const int f = w / M, n = w - f * M;
+            const int s0 = (t0 + f) * p.hop + 2 * n;
+            float2 v;
+            v.x = s0 < p.sample_count ? __ldg(xs + s0) * __ldg(p.window + 2 * n) : 0.f;
+            v.y = s0 + 1 < p.sample_count ? __ldg(xs + s0 + 1) * __ldg(p.window + 2 * n + 1) : 0.f;
+            buf0[w] = v;
+        }
+        __syncthreads();
+        float2* src = buf0;
+        float2* dst = buf1;
+        int Ns = 1;
+        for (int st = 0; st < p.n_stages; ++st) {
+            const int R = p.radix[st];
+            if (R == 4) stockham_stage<4>(src, dst, tw, M, Ns, F);
+            else if (R == 2) stockham_stage<2>(src, dst, tw, M, Ns, F);
+            else if (R == 5) stockham_stage<5>(src, dst, tw, M, Ns, F);
+            else stockham_stage<3>(src, dst, tw, M, Ns, F);
+            Ns *= R;
+            __syncthreads();
+            float2* t = src; src = dst; dst = t;
+        }
+        // |X[k]|, k = 0..M, into the free buffer as float mag[f][bins]
+        float* mag = reinterpret_cast<float*>(dst);              // F * (M + 1) floats <= F * M float2
+        for (int w = threadIdx.x; w < F * bins; w += LM_THREADS) {
+            const int f = w / bins, k = w - f * bins;
+            const float2 z = src[f * M + (k == M ? 0 : k)];
+            const float2 zc = src[f * M + (k == 0 || k == M ? 0 : M - k)];
+            const float er = 0.5f * (z.x + zc.x), ei = 0.5f * (z.y - zc.y);     // E[k]
+            const float orr = 0.5f * (z.y + zc.y), oi = -0.5f * (z.x - zc.x);   // O[k] = -i (Z - conj Zc) / 2
+            const float2 wk = tw[k];
+            const float xr = er + (orr * wk.x - oi * wk.y);
+            const float xi = ei + (orr * wk.y + oi * wk.x);
+            mag[w] = sqrtf(xr * xr + xi * xi);
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < F * p.n_mels; w += LM_THREADS) {
+            const int f = w / p.n_mels, m = w - f * p.n_mels;
+            const int lo = __ldg(p.mel_lo + m), cnt = __ldg(p.mel_cnt + m);
+            const float* wt = p.mel_w + __ldg(p.mel_off + m);
+            const float* mg = mag + f * bins + lo;
+            float s = 0.f;
+            for (int i = 0; i < cnt; ++i) s = fmaf(mg[i], __ldg(wt + i), s);
+            const float y = p.log_scale * logf(s + p.log_floor);
+            const size_t o = ((size_t)b * p.n_frames + t0 + f) * p.n_mels + m;
+            const __half h = __float2half_rn(y);
+            p.out.hi[o] = h;
+            p.out.hi[p.out.plane + o] = __float2half_rn(y - __half2float(h));
+            if (p.out_f32) p.out_f32[o] = y;
+        }
+    }
+}
+
+}  // namespace
+
+size_t logmel_smem_bytes(int n_fft) { return (size_t)(n_fft + 2 * LM_FRAMES * (n_fft / 2)) * sizeof(float2); }
+
+bool logmel_factorize(int n_fft, int radix[8], int* n_stages) {
+    if (n_fft < 8 || (n_fft & 1)) return false;
+    int m = n_fft / 2, n = 0;
+    const int cand[4] = {4, 2, 5, 3};
+    for (int ci = 0; ci < 4; ++ci)
+        while (m % cand[ci] == 0) {
+            if (n >= 8) return false;
+            radix[n++] = cand[ci];
+            m /= cand[ci];
+        }
+    *n_stages = n;
+    return m == 1;
+}
+
+void logmel_twiddles(int n_fft, std::vector<float>& out) {
+    out.resize((size_t)2 * n_fft);
+    for (int i = 0; i < n_fft; ++i) {
+        const double a = -2.0 * M_PI * (double)i / (double)n_fft;
+        out[2 * i] = (float)cos(a);
+        out[2 * i + 1] = (float)sin(a);
+    }
+}
+
+cudaError_t logmel_init_device() {
+    return cudaFuncSetAttribute(k_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+cudaError_t launch_logmel(const LogmelParams& p, cudaStream_t stream) {
+    if (p.batch <= 0) return cudaSuccess;
+    const size_t smem = logmel_smem_bytes(p.n_fft);
+    if (smem > 96 * 1024 || p.n_stages < 1 || p.n_stages > 8) return cudaErrorInvalidValue;
+    const int per_cta = LM_FRAMES * LM_PASSES;
+    dim3 grid((unsigned)((p.n_frames + per_cta - 1) / per_cta), (unsigned)p.batch);
+    k_logmel<<<grid, LM_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace bn

@@ -785,9 +785,8 @@ cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream) {
 // ======================================================================================
 // CTA = one strip of STRIP output pixels of one output row; the k input rows it needs are staged
 // in smem as FP32; thread = (pixel slot, channel quad) with its k*k*cin x 4 weights in registers.
-template <int K, int CIN, int STRIDE>
+template <int K, int CIN, int STRIDE, int STRIP>
 __global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
-    constexpr int STRIP = 128;
     constexpr int WIN = (STRIP - 1) * STRIDE + K;               // input columns per strip
     __shared__ float s_x[K][WIN * CIN];
     const int quads = p.cout >> 2;                               // 8 for cout = 32
@@ -810,14 +809,16 @@ __global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
     const int ix_base = ox0 * STRIDE - p.pad, iy_base = oy * STRIDE - p.pad;
     const size_t in_base = (size_t)b * p.hin * p.win * CIN;
     __syncthreads();                                                   // previous strip fully consumed
-    // stage K rows x WIN pixels: one 4-byte (2-channel) load per pixel and plane, all loads of a
-    // thread issued before any shared-memory store so their latencies overlap
-    static_assert(CIN == 2, "pixel = one 32-bit word per plane");
+    // stage K rows x WIN pixels: one 4-byte (2-channel) or 2-byte (1-channel) load per pixel and
+    // plane, all loads of a thread issued before any shared-memory store so their latencies overlap
+    static_assert(CIN == 1 || CIN == 2, "pixel = one 16/32-bit word per plane");
     constexpr int NPIX = K * WIN;
     constexpr int NLD = (NPIX + 255) / 256;
     uint32_t vh[NLD], vl[NLD];
     const uint32_t* ph32 = reinterpret_cast<const uint32_t*>(p.in.hi);
     const uint32_t* pl32 = reinterpret_cast<const uint32_t*>(p.in.hi + p.in.plane);
+    const unsigned short* ph16 = reinterpret_cast<const unsigned short*>(p.in.hi);
+    const unsigned short* pl16 = reinterpret_cast<const unsigned short*>(p.in.hi + p.in.plane);
 #pragma unroll
     for (int j = 0; j < NLD; ++j) {
         const int i = threadIdx.x + j * 256;
@@ -825,9 +826,15 @@ __global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
         const int iy = iy_base + ky, ix = ix_base + x;
         vh[j] = 0u; vl[j] = 0u;
         if (i < NPIX && iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win) {
-            const size_t o = (in_base >> 1) + (size_t)iy * p.win + ix;
-            vh[j] = __ldg(ph32 + o);
-            vl[j] = __ldg(pl32 + o);
+            if (CIN == 2) {
+                const size_t o = (in_base >> 1) + (size_t)iy * p.win + ix;
+                vh[j] = __ldg(ph32 + o);
+                vl[j] = __ldg(pl32 + o);
+            } else {
+                const size_t o = in_base + (size_t)iy * p.win + ix;
+                vh[j] = __ldg(ph16 + o);
+                vl[j] = __ldg(pl16 + o);
+            }
         }
     }
 #pragma unroll
@@ -837,8 +844,12 @@ __global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
             const int ky = i / WIN, x = i - ky * WIN;
             const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vh[j]));
             const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&vl[j]));
-            s_x[ky][x * 2] = a.x + d.x;
-            s_x[ky][x * 2 + 1] = a.y + d.y;
+            if (CIN == 2) {
+                s_x[ky][x * 2] = a.x + d.x;
+                s_x[ky][x * 2 + 1] = a.y + d.y;
+            } else {
+                s_x[ky][x] = a.x + d.x;
+            }
         }
     }
     __syncthreads();
@@ -872,12 +883,19 @@ __global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
 
 cudaError_t launch_stem_planes(const ConvPlanesParams& p, cudaStream_t stream) {
     if (p.batch <= 0) return cudaSuccess;
-    if (p.k != 3 || p.cin != 2 || p.stride != 2 || (p.cout & 3) || p.cout > 64 || (256 % (p.cout >> 2)) || p.in_scale || p.residual.hi)
+    if (p.k != 3 || (p.cin != 2 && p.cin != 1) || p.stride != 2 || (p.cout & 3) || p.cout > 64 || (256 % (p.cout >> 2)) || p.in_scale || p.residual.hi)
         return cudaErrorInvalidValue;
-    const int strips = (p.wout + 127) / 128;
+    const int strip = p.wout > 64 ? 128 : 64;
+    const int strips = (p.wout + strip - 1) / strip;
     const long long total = (long long)p.batch * p.hout * strips;
     const int grid = (int)(total < 148 * 6 ? total : 148 * 6);
-    k_stem_planes<3, 2, 2><<<grid, 256, 0, stream>>>(p);
+    if (p.cin == 2) {
+        if (strip == 128) k_stem_planes<3, 2, 2, 128><<<grid, 256, 0, stream>>>(p);
+        else k_stem_planes<3, 2, 2, 64><<<grid, 256, 0, stream>>>(p);
+    } else {
+        if (strip == 128) k_stem_planes<3, 1, 2, 128><<<grid, 256, 0, stream>>>(p);
+        else k_stem_planes<3, 1, 2, 64><<<grid, 256, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

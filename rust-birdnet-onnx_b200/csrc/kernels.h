@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 namespace bn {
 
@@ -105,6 +106,28 @@ struct SeParams {
     int c, r, ldw1, ldw2, npix;
 };
 cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream);
+
+// ---- log-mel front-end (row A9: BirdNET v3.0 / Perch v2), frontend_logmel.cu -------------------
+struct LogmelParams {
+    const float* audio;       // [B][sample_count] raw samples
+    int batch, sample_count;
+    const float* window;      // [n_fft]
+    const float2* twiddle;    // [n_fft] exp(-2*pi*i*m/n_fft), built in float64
+    const int* mel_lo;        // [n_mels] first bin of the filter
+    const int* mel_cnt;       // [n_mels] bins in the filter
+    const int* mel_off;       // [n_mels] offset of its weights in mel_w
+    const float* mel_w;       // packed filter weights
+    int n_fft, hop, n_frames, n_mels;
+    int radix[8], n_stages;   // factorisation of n_fft / 2
+    float log_floor, log_scale;
+    PlanesPtr out;            // [B][n_frames][n_mels] hi/lo planes
+    float* out_f32;           // optional FP32 copy of the same layout, or nullptr
+};
+cudaError_t logmel_init_device();
+size_t logmel_smem_bytes(int n_fft);
+bool logmel_factorize(int n_fft, int radix[8], int* n_stages);
+cudaError_t launch_logmel(const LogmelParams& p, cudaStream_t stream);
+void logmel_twiddles(int n_fft, std::vector<float>& out);   // interleaved re/im
 
 // ---- epilogue (rows A4 / A6) ------------------------------------------------------
 struct TopkParams {

@@ -114,6 +114,12 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((row_bytes * 8u) >> 4) << 32) |
            (1ull << 46) | (layout << 61);
 }
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices, rows of a core matrix 16 B apart;
+// lbo = bytes between the two core matrices one K=16 step spans, sbo = bytes between 8-row groups.
+// With sbo = 128 the A rows are a plain 16-byte-pitch array, so a row shift is a start-address shift.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
 // 5-D tiled TMA load global -> shared, completion (bytes) on an mbarrier (SASS: UTMALDG)
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
     asm volatile(

@@ -6,12 +6,12 @@
 // bits) and every K step issues three kind::f16 MMAs (hi*hi + hi*lo + lo*hi) into one FP32 TMEM
 // accumulator; the dropped lo*lo term is ~2^-22 relative.  See DESIGN.md "precision policy".
 //
-// Persistent, warp-specialised CTA (288 threads, one per SM), static round-robin tile schedule:
+// Persistent, warp-specialised CTA (416 threads, one or two per SM), static round-robin tile schedule:
 //   warps 0-3  A producers: im2col gather of the 128-row tile straight from the hi/lo planes with
 //              16-byte cp.async (zero-fill for padding) into SWIZZLE_128B K-major smem; thread 0
 //              also issues one 1-D bulk copy (TMA engine) per K chunk for the pre-swizzled weights
 //   warp  4    owns TMEM; lane 0 issues tcgen05.mma and commits stage/accumulator barriers
-//   warps 5-8  epilogue: tcgen05.ld -> bias / SiLU / sigmoid / residual -> split -> global planes
+//   warps 5-12 epilogue: tcgen05.ld -> bias / SiLU / sigmoid / residual -> split -> global planes
 // Two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 // smem ring: STAGES x { A_hi 16 KB | A_lo 16 KB | W_hi NT*128 B | W_lo NT*128 B }.
 #include "tc_common.cuh"
@@ -26,7 +26,11 @@ constexpr int MAX_STAGES = 6;
 constexpr int MAX_K_CHUNKS = 64;     // K <= 4096
 constexpr int MAX_SMEM_BIAS = 1536;
 constexpr int A_TILE_BYTES = TM * 128;
-constexpr int NTHREADS = 288;
+constexpr int HALO_W = TM + 2;               // patch columns (one 128-pixel run of an image row + halo)
+constexpr int HALO_PIX = 3 * HALO_W;           // patch pixels: 3 input rows
+constexpr int MAX_HALO_SLOTS = 3;
+constexpr int EPI_WARPS = 8;         // two warps per TMEM lane quarter, interleaved 16-column groups
+constexpr int NTHREADS = (5 + EPI_WARPS) * 32;
 
 __device__ __forceinline__ float act_fn(float v, int act) {
     if (act == KACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
@@ -58,6 +62,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     __shared__ __align__(8) uint64_t bar_acc_full[2];
     __shared__ __align__(8) uint64_t bar_acc_empty[2];
     __shared__ uint32_t tmem_holder;
+    __shared__ __align__(8) uint64_t bar_w;         // HALO: resident weights landed
     __shared__ int2 tap_tab[MAX_K_CHUNKS * 8];
     __shared__ float s_bias[MAX_SMEM_BIAS];
 
@@ -71,12 +76,13 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             // cp.async modes: 128 producer threads + thread 0's expect_tx arrive; TMA: thread 0 only
-            mbar_init(&bar_full[s], MODE == TC_IN_TMA ? 1 : 129);
+            mbar_init(&bar_full[s], MODE == TC_IN_TMA ? 1 : (MODE == TC_IN_HALO ? 128 : 129));
             mbar_init(&bar_empty[s], 1);       // tcgen05.commit
         }
+        mbar_init(&bar_w, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_acc_full[a], 1);    // tcgen05.commit
-            mbar_init(&bar_acc_empty[a], 4);   // one arrive per epilogue warp
+            mbar_init(&bar_acc_empty[a], EPI_WARPS);   // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -104,7 +110,50 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
 
-    if (MODE == TC_IN_TMA && warp < 4) {
+    // HALO geometry: [resident W: k_chunks x w_bytes][slot 0][slot 1][slot 2]; a slot holds the hi and
+    // the lo patch, each [cin/8][HALO_PIX] 16-byte cells (channel-group major, pixels at 16-byte pitch)
+    const uint32_t halo_plane_bytes = (uint32_t)(p.cin >> 3) * HALO_PIX * 16u;
+    const uint32_t halo_slot_bytes = (2u * halo_plane_bytes + 1023u) & ~1023u;
+    uint8_t* halo_slots = tiles + (size_t)p.k_chunks * w_bytes;
+    if (MODE == TC_IN_HALO && warp < 4) {
+        // ================================ halo-patch producers ================================
+        const int n_tile = blockIdx.x % p.n_tiles;               // fixed per CTA (grid % n_tiles == 0)
+        if (tid == 0) {
+            asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
+                         ::"r"(smem_u32(&bar_w)), "r"((uint32_t)p.k_chunks * w_bytes) : "memory");
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)n_tile * p.k_chunks + kc) * w_bytes;
+                bulk_copy_g2s(tiles + (size_t)kc * w_bytes, src, w_bytes, &bar_w);
+            }
+        }
+        const int J = p.cin >> 3;
+        const int cells = J * HALO_PIX;                          // 16-byte cells per plane
+        const __half* in_lo = p.in_hi + p.in_plane;
+        const int hw = p.hout * p.wout;
+        uint32_t s = 0, ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m0 = (t / p.n_tiles) * TM;
+            const int b = m0 / hw, rem = m0 - b * hw;
+            const int oy = rem / p.wout, ox0 = rem - oy * p.wout;
+            mbar_wait(&bar_empty[s], ph ^ 1u);
+            const uint32_t d0 = smem_u32(halo_slots + (size_t)s * halo_slot_bytes);
+            const int seg_base = b * p.seg_stride;
+            for (int e = tid; e < cells; e += 128) {
+                const int pix = e / J, j = e - pix * J;          // consecutive lanes: the J cells of a pixel, then the next pixel
+                const int r = pix / HALO_W, x = pix - r * HALO_W;
+                const int iy = oy - 1 + r, ix = ox0 - 1 + x;
+                const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win;
+                const int eo = ok ? seg_base + (iy * p.win + ix) * p.cin + j * 8 : 0;
+                const uint32_t nb = ok ? 16u : 0u;
+                const uint32_t d = d0 + (uint32_t)(j * HALO_PIX + pix) * 16u;
+                cp_async16(d, p.in_hi + eo, nb);
+                cp_async16(d + halo_plane_bytes, in_lo + eo, nb);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+            if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+        }
+        cp_async_wait_all();
+    } else if (MODE == TC_IN_TMA && warp < 4) {
         // ================================ TMA producer (one thread) ================================
         if (tid == 0) {
             tma_prefetch_desc(&p.tmap);
@@ -261,7 +310,45 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         if (MODE == TC_IN_PLANES) cp_async_wait_all();   // nothing may be in flight when the CTA exits
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        if (MODE == TC_IN_HALO && lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(TM, NT);
+            const uint32_t lbo = HALO_PIX * 16u;                 // next 8-channel group of the same pixels
+            const int ksteps = p.cin >> 4;
+            mbar_wait(&bar_w, 0);
+            uint32_t s = 0, ph = 0, it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const uint32_t a = it & 1u;
+                mbar_wait(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u);
+                mbar_wait(&bar_full[s], ph);
+                fence_proxy_async_smem();
+                tc_fence_after();
+                const uint32_t acc = tmem_base + a * (uint32_t)NT;
+                const uint32_t a_hi = smem_u32(halo_slots + (size_t)s * halo_slot_bytes);
+                const uint32_t w0 = smem_u32(tiles);
+                uint32_t first = 0;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const uint32_t shift = (uint32_t)(ky * HALO_W + kx) * 16u;      // row m <-> patch pixel m + ky*130 + kx
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const int k = tap * p.cin + ks * 16;
+                        const uint32_t wb = w0 + (uint32_t)(k >> 6) * w_bytes;
+                        const uint64_t adv = (uint64_t)(kDescKStep * ((k & 63) >> 4));
+                        const uint64_t db_hi = umma_desc_sw128(wb) + adv;
+                        const uint64_t db_lo = umma_desc_sw128(wb + (uint32_t)NT * 128u) + adv;
+                        const uint32_t a_off = (uint32_t)(2 * ks) * lbo + shift;
+                        const uint64_t da_hi = umma_desc_nosw(a_hi + a_off, lbo, 128u);
+                        const uint64_t da_lo = umma_desc_nosw(a_hi + halo_plane_bytes + a_off, lbo, 128u);
+                        umma_f16(acc, da_hi, db_hi, idesc, first);
+                        umma_f16(acc, da_hi, db_lo, idesc, 1u);
+                        umma_f16(acc, da_lo, db_hi, idesc, 1u);
+                        first = 1u;
+                    }
+                }
+                umma_commit(&bar_empty[s]);
+                umma_commit(&bar_acc_full[a]);
+                if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
+            }
+        } else if (MODE != TC_IN_HALO && lane == 0) {
             const uint32_t idesc = umma_idesc_f16(TM, NT);
             const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
             uint32_t s = 0, ph = 0, it = 0;
@@ -301,6 +388,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     } else {
         // ================================ epilogue ================================
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int cgrp = (warp - 5) >> 2;              // which interleaved set of 16-column groups
         uint32_t it = 0;
         const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -319,7 +407,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 const int b = row / p.spec_nframes, tt = row - b * p.spec_nframes;
                 spec_base = ((size_t)b * p.cout * p.spec_nframes + tt) * p.spec_nch + p.spec_ch;
             }
-            for (int c0 = 0; c0 < NT; c0 += 16) {
+            for (int c0 = cgrp * 16; c0 < NT; c0 += 16 * (EPI_WARPS / 4)) {
                 float v[16];
                 __syncwarp();                          // tcgen05.ld is .sync.aligned: reconverge first
                 tmem_ld16(t_lane + (uint32_t)c0, v);
@@ -406,6 +494,19 @@ size_t tc_conv_smem_bytes(int nt, int stages) {
     return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)nt * 128) + 1024;
 }
 
+size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots) {
+    const size_t plane = (size_t)(cin / 8) * HALO_PIX * 16;
+    const size_t slot = (2 * plane + 1023) & ~(size_t)1023;
+    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024;
+}
+
+int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks) {
+    if (k != 3 || stride != 1 || pad != 1 || (cin & 15) || wout != win || (wout % TM) != 0) return 0;
+    for (int s = MAX_HALO_SLOTS; s >= 2; --s)
+        if (tc_conv_halo_smem_bytes(cin, nt, k_chunks, s) <= 200 * 1024) return s;
+    return 0;
+}
+
 int tc_conv_pick_stages(int nt, int k_chunks) {
     (void)k_chunks;                     // the ring runs across tiles, so depth is useful even for K <= 64
     // prefer two CTAs per SM (<= 104 KB each) when at least two stages fit, else one deep ring
@@ -424,6 +525,8 @@ cudaError_t tc_conv_init_device() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_tc_conv<TC_IN_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_tc_conv<TC_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
 }
 
@@ -439,6 +542,19 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
         p.tmem_cols < 2 * p.nt || p.tmem_cols > 512)
         return cudaErrorInvalidValue;
     const int total = p.m_tiles * p.n_tiles;
+    if (p.in_mode == TC_IN_HALO) {
+        // p.stages = patch slots (tc_conv_halo_slots); every CTA keeps one n tile's weights resident
+        if (p.stages < 2 || p.stages > MAX_HALO_SLOTS || p.k != 3 || p.stride != 1 || p.pad != 1 || (p.cin & 15) ||
+            (p.wout % TM) != 0 || p.win != p.wout || p.K != 9 * p.cin)
+            return cudaErrorInvalidValue;
+        const size_t hs = tc_conv_halo_smem_bytes(p.cin, p.nt, p.k_chunks, p.stages);
+        if (hs > 208 * 1024) return cudaErrorInvalidValue;
+        int g = total < num_sms ? total : num_sms;
+        g -= g % p.n_tiles;
+        if (g <= 0) return cudaErrorInvalidValue;
+        k_tc_conv<TC_IN_HALO><<<g, NTHREADS, hs, stream>>>(p);
+        return cudaGetLastError();
+    }
     size_t smem = tc_conv_smem_bytes(p.nt, p.stages);
     // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
     const int per_sm = ((p.in_mode == TC_IN_PLANES || p.in_mode == TC_IN_TMA) && smem <= 104 * 1024 && p.tmem_cols <= 256) ? 2 : 1;

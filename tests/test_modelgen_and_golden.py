@@ -87,3 +87,35 @@ def test_layer_table_totals(v24_spec):
     macs = sum(r["macs"] for r in rows)
     assert 0.55e9 < macs < 0.65e9 and v24_spec.frontend_macs() == 511 * 96 * (2048 + 1024)
     assert abs(sum(r["w_elems"] for r in rows) * 4 / 1e6 - 42.8) < 1.0     # "~50 MB weights" datapoint
+
+
+# ------------------------------------------------------------------ 32 kHz families (row A9)
+@pytest.mark.parametrize("fam,gold,mt,emb,nsp,outs", [
+    ("birdnet_v30", "v30_seed0.npz", 1, 1024, 11560, [b"output_0", b"output_1"]),
+    ("perch_v2", "perch_seed0.npz", 2, 1536, 14795, None),
+])
+def test_32k_families_parse_and_reproduce_golden(fam, gold, mt, emb, nsp, outs):
+    from birdnet_b200.modelgen.make_models import ensure_model
+    from oracle.model_oracle import ModelOracle, load_initializers
+    from oracle import postprocess_oracle as po
+    path = ensure_model(fam)
+    spec = get_spec(fam)
+    info = _ffi.IoInfo()
+    assert _ffi.lib.bn_model_inspect(path.encode(), -1, C.byref(info)) == 0, _ffi.last_error()
+    assert (info.model_type, info.sample_count, info.num_species, info.embedding_dim) == (mt, 160000, nsp, emb)
+    assert info.sample_rate == 32000 and info.segment_duration == 5.0          # types.rs:17-31
+    if outs is not None:                                                        # batch_context.rs:252-262
+        assert [info.outputs[i].name for i in range(info.n_outputs)] == outs
+    else:                                                                       # detection.rs:214-232
+        assert info.n_outputs == 4
+        assert [info.outputs[i].shape()[1:] for i in range(4)] == [[1536], [16, 4, 1536], [500, 128], [14795]]
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), gold))
+    h = hashlib.sha256(open(path, "rb").read()).digest()
+    assert np.array_equal(np.frombuffer(h, dtype=np.uint8), g["model_sha256"])
+    audio = synth.batch(0, 3, 160000, 32000)
+    logits, e = ModelOracle(spec, load_initializers(path)).logits_and_embeddings(audio)
+    assert np.abs(logits[:, ::32] - g["logits_every_32"][:3]).max() < 2e-3
+    assert np.abs(e[:, ::8] - g["emb_every_8"][:3]).max() < 1e-3
+    _, conf, counts = po.top_k_batch(logits, 5, 0.1)
+    assert np.array_equal(counts, g["top5_count"][:3])
+    assert np.abs(conf - g["top5_conf"][:3]).max() < 1e-3
