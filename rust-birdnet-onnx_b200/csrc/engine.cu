@@ -135,11 +135,11 @@ static void build_real_mel_basis(const SpecBranch& br, std::vector<float>& basis
     }
 }
 
-// UMMA N for a layer: the largest multiple of 16 (<= 256) that divides cout rounded up to 16
+// UMMA N tile for a layer: the largest multiple of 16 (<= 128) that divides cout rounded up to 16
 static int choose_nt(int cout) {
     const int c16 = (cout + 15) / 16 * 16;
     int best = 16;
-    for (int nt = 16; nt <= 256; nt += 16)
+    for (int nt = 16; nt <= 128; nt += 16)      // N = 2*NT per MMA (main | correction accumulators) must stay <= 256
         if (c16 % nt == 0) best = nt;
     return best;
 }
@@ -207,9 +207,9 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             std::vector<uint16_t> pack;
             tc_pack_weights(op.weight.data(), K, op.cout, op.ldw, d.nt, pack, &d.n_tiles, &d.k_chunks);
             d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks);
-            while (d.stages > 2 && tc_conv_smem_bytes(d.nt, d.stages) > 208 * 1024) --d.stages;
+            while (d.stages > 2 && tc_conv_smem_bytes(d.nt, d.stages, 8) > 220 * 1024) --d.stages;
             d.tmem_cols = 32;
-            while (d.tmem_cols < 2 * d.nt) d.tmem_cols <<= 1;
+            while (d.tmem_cols < 4 * d.nt) d.tmem_cols <<= 1;      // 2 buffers x (main | correction)
             BN_CUDA(cudaMalloc(&d.wpack, pack.size() * sizeof(uint16_t)));
             BN_CUDA(cudaMemcpy(d.wpack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
             d.use_tc = true;
@@ -249,7 +249,7 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
                 tc_pack_weights(wb.data(), ft.K, br.n_mels, ldb, ft.nt, pack, &ft.n_tiles, &ft.k_chunks);
                 ft.stages = tc_conv_pick_stages(ft.nt, ft.k_chunks);
                 ft.tmem_cols = 32;
-                while (ft.tmem_cols < 2 * ft.nt) ft.tmem_cols <<= 1;
+                while (ft.tmem_cols < 4 * ft.nt) ft.tmem_cols <<= 1;
                 BN_CUDA(cudaMalloc(&ft.wpack, pack.size() * sizeof(uint16_t)));
                 BN_CUDA(cudaMemcpy(ft.wpack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
                 e->fe_tc.push_back(ft);

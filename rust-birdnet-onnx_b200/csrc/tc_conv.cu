@@ -24,13 +24,14 @@ constexpr int TM = 128;           // UMMA M (one TMEM lane per output row)
 constexpr int KC = 64;            // K elements per smem stage = one 128-byte swizzle row of fp16
 constexpr int MAX_STAGES = 6;
 constexpr int MAX_K_CHUNKS = 64;     // K <= 4096
-constexpr int MAX_SMEM_BIAS = 1536;
+constexpr int MAX_SMEM_BIAS = 256;      // layers with more output channels read the bias through L1
+constexpr int EPI_STAGE_BYTES = 4096;    // per epilogue warp: 32 rows x 32 FP32 columns
 constexpr int A_TILE_BYTES = TM * 128;
 constexpr int HALO_W = TM + 2;               // patch columns (one 128-pixel run of an image row + halo)
 constexpr int HALO_PIX = 3 * HALO_W;           // patch pixels: 3 input rows
 constexpr int MAX_HALO_SLOTS = 3;
-constexpr int EPI_WARPS = 8;         // two warps per TMEM lane quarter, interleaved 16-column groups
-constexpr int NTHREADS = (5 + EPI_WARPS) * 32;
+constexpr int MAX_EPI_WARPS = 8;     // 8 (one CTA per SM) or 4 (two CTAs per SM): warps 5.. of the CTA
+constexpr int NTHREADS = (5 + MAX_EPI_WARPS) * 32;
 
 __device__ __forceinline__ float act_fn(float v, int act) {
     if (act == KACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
@@ -63,11 +64,13 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     __shared__ __align__(8) uint64_t bar_acc_empty[2];
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(8) uint64_t bar_w;         // HALO: resident weights landed
-    __shared__ int2 tap_tab[MAX_K_CHUNKS * 8];
+    __shared__ uint32_t tap_tab[MAX_K_CHUNKS * 8];   // (element offset << 5) | tap bit
     __shared__ float s_bias[MAX_SMEM_BIAS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.nt, STAGES = p.stages;
+    const int nthreads = (int)blockDim.x;
+    const int epi_warps = (nthreads >> 5) - 5;
     const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)NT * 128u;
     const uint32_t w_bytes = 2u * (uint32_t)NT * 128u;
     const int total_tiles = p.m_tiles * p.n_tiles;
@@ -82,29 +85,25 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         mbar_init(&bar_w, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_acc_full[a], 1);    // tcgen05.commit
-            mbar_init(&bar_acc_empty[a], EPI_WARPS);   // one arrive per epilogue warp
+            mbar_init(&bar_acc_empty[a], (uint32_t)epi_warps);   // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc(&tmem_holder, p.tmem_cols);
     // K unit -> (tap element offset, tap bit) table, shared by all tiles of this CTA
-    for (int u = tid; u < p.k_chunks * 8; u += NTHREADS) {
+    for (int u = tid; u < p.k_chunks * 8; u += nthreads) {
         const int k0 = u * 8;
-        int2 e;
+        uint32_t e = 31u;                          // tap 31 is never set in a row mask -> zero fill
         if (k0 < p.K) {
             const int tap = k0 / p.tab_cin, ci = k0 - tap * p.tab_cin;
             const int ky = tap / p.k, kx = tap - ky * p.k;
-            e.x = (ky * p.win + kx) * p.pix_stride + ci;
-            e.y = tap;
-        } else {
-            e.x = 0;
-            e.y = 31;                              // never set in a row mask -> zero fill
+            e = ((uint32_t)((ky * p.win + kx) * p.pix_stride + ci) << 5) | (uint32_t)tap;
         }
         tap_tab[u] = e;
     }
     const bool s_bias_ok = p.bias != nullptr && p.cout <= MAX_SMEM_BIAS;
     if (s_bias_ok)
-        for (int i = tid; i < p.cout; i += NTHREADS) s_bias[i] = p.bias[i];
+        for (int i = tid; i < p.cout; i += nthreads) s_bias[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -115,6 +114,9 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     const uint32_t halo_plane_bytes = (uint32_t)(p.cin >> 3) * HALO_PIX * 16u;
     const uint32_t halo_slot_bytes = (2u * halo_plane_bytes + 1023u) & ~1023u;
     uint8_t* halo_slots = tiles + (size_t)p.k_chunks * w_bytes;
+    // the epilogue staging tiles start after the ring
+    const size_t ring_bytes = MODE == TC_IN_HALO ? (size_t)p.k_chunks * w_bytes + (size_t)STAGES * halo_slot_bytes
+                                                 : (size_t)STAGES * stage_bytes;
     if (MODE == TC_IN_HALO && warp < 4) {
         // ================================ halo-patch producers ================================
         const int n_tile = blockIdx.x % p.n_tiles;               // fixed per CTA (grid % n_tiles == 0)
@@ -251,7 +253,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                                          ((size_t)n_tile * p.k_chunks + kc) * w_bytes;
                     bulk_copy_g2s(st + 2 * A_TILE_BYTES, src, w_bytes, &bar_full[s]);
                 }
-                const int2 te = tap_tab[kc * 8 + unit];   // x: element offset of (tap, ci); y: tap bit (31 = beyond K)
+                int2 te;                                  // x: element offset of (tap, ci); y: tap bit (31 = beyond K)
+                { const uint32_t tt = tap_tab[kc * 8 + unit]; te.x = (int)(tt >> 5); te.y = (int)(tt & 31u); }
                 if (MODE == TC_IN_PLANES) {
                     const uint32_t d = smem_u32(st) + dst0;
 #pragma unroll
@@ -310,8 +313,13 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         if (MODE == TC_IN_PLANES) cp_async_wait_all();   // nothing may be in flight when the CTA exits
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
+        // Accumulator a = TMEM columns [a*2NT, a*2NT + 2NT): [main = A_hi*W_hi | corr = A_hi*W_lo + A_lo*W_hi].
+        // The tensor core truncates when it adds into the FP32 accumulator; keeping the 2^-11-sized
+        // correction terms out of the big accumulator cuts the number of truncating adds 3x and the
+        // epilogue adds main + corr once, round-to-nearest.  W_hi and W_lo tiles are adjacent in smem,
+        // so A_hi * [W_hi | W_lo] is ONE MMA of N = 2NT.
         if (MODE == TC_IN_HALO && lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(TM, NT);
+            const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint32_t lbo = HALO_PIX * 16u;                 // next 8-channel group of the same pixels
             const int ksteps = p.cin >> 4;
             mbar_wait(&bar_w, 0);
@@ -322,7 +330,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 mbar_wait(&bar_full[s], ph);
                 fence_proxy_async_smem();
                 tc_fence_after();
-                const uint32_t acc = tmem_base + a * (uint32_t)NT;
+                const uint32_t acc = tmem_base + a * 2u * (uint32_t)NT;
                 const uint32_t a_hi = smem_u32(halo_slots + (size_t)s * halo_slot_bytes);
                 const uint32_t w0 = smem_u32(tiles);
                 uint32_t first = 0;
@@ -334,13 +342,11 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         const uint32_t wb = w0 + (uint32_t)(k >> 6) * w_bytes;
                         const uint64_t adv = (uint64_t)(kDescKStep * ((k & 63) >> 4));
                         const uint64_t db_hi = umma_desc_sw128(wb) + adv;
-                        const uint64_t db_lo = umma_desc_sw128(wb + (uint32_t)NT * 128u) + adv;
                         const uint32_t a_off = (uint32_t)(2 * ks) * lbo + shift;
                         const uint64_t da_hi = umma_desc_nosw(a_hi + a_off, lbo, 128u);
                         const uint64_t da_lo = umma_desc_nosw(a_hi + halo_plane_bytes + a_off, lbo, 128u);
-                        umma_f16(acc, da_hi, db_hi, idesc, first);
-                        umma_f16(acc, da_hi, db_lo, idesc, 1u);
-                        umma_f16(acc, da_lo, db_hi, idesc, 1u);
+                        umma_f16(acc, da_hi, db_hi, idesc2, first);
+                        umma_f16(acc + (uint32_t)NT, da_lo, db_hi, idesc1, 1u);
                         first = 1u;
                     }
                 }
@@ -349,21 +355,20 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
             }
         } else if (MODE != TC_IN_HALO && lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(TM, NT);
+            const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const uint32_t a = it & 1u;
                 mbar_wait(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + a * (uint32_t)NT;
+                const uint32_t acc = tmem_base + a * 2u * (uint32_t)NT;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&bar_full[s], ph);
                     fence_proxy_async_smem();          // cp.async / st.shared (generic proxy) -> tcgen05 reads (async proxy)
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t db_hi = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES);
-                    const uint64_t db_lo = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES + (uint32_t)NT * 128u);
+                    const uint64_t db_hi = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES);   // [W_hi | W_lo]: 2NT rows
                     int ksteps = (p.K - kc * KC + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
                     for (int j = 0; j < ksteps; ++j) {
@@ -374,9 +379,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         const uint64_t da_hi = umma_desc_kmajor(a_hi + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
                         const uint64_t da_lo = umma_desc_kmajor(a_hi + A_TILE_BYTES + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
                         const uint64_t adv = (uint64_t)(kDescKStep * j);
-                        umma_f16(acc, da_hi, db_hi + adv, idesc, (kc | j) != 0 ? 1u : 0u);
-                        umma_f16(acc, da_hi, db_lo + adv, idesc, 1u);
-                        umma_f16(acc, da_lo, db_hi + adv, idesc, 1u);
+                        umma_f16(acc, da_hi, db_hi + adv, idesc2, (kc | j) != 0 ? 1u : 0u);
+                        umma_f16(acc + (uint32_t)NT, da_lo, db_hi + adv, idesc1, 1u);
                     }
                     umma_commit(&bar_empty[s]);        // frees the smem stage when these MMAs retire
                     if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
@@ -387,88 +391,131 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         __syncwarp();
     } else {
         // ================================ epilogue ================================
+        // Phase 1 (lane = output row = TMEM lane): main + corr + bias, activation, FP32 into this warp's
+        // staging tile [32 rows][32 columns] (16-byte chunks XOR-swizzled by row & 7).
+        // Phase 2 (lanes along the channel axis): + residual, hi/lo split, 16-byte stores that cover
+        // whole 32/64-byte row pieces (full sectors) instead of one 16-byte piece in each of 32 lines.
+        const int ew = warp - 5;
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int cgrp = (warp - 5) >> 2;              // which interleaved set of 16-column groups
+        const int cset = ew >> 2, nsets = epi_warps >> 2;
+        float* stg = reinterpret_cast<float*>(tiles + ring_bytes + (size_t)ew * EPI_STAGE_BYTES);
         uint32_t it = 0;
         const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
+        const bool staged = vec && p.out_f32 == nullptr && p.spec_nframes == 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int mt = p.n_tiles == 1 ? t : t / p.n_tiles;
             const int n_tile = p.n_tiles == 1 ? 0 : t - mt * p.n_tiles;
             const int sb = mt / p.tiles_per_seg, lt = mt - sb * p.tiles_per_seg;
-            const int lp = lt * TM + q * 32 + lane;            // row inside the segment
+            const int lp0 = lt * TM + q * 32;                  // first row of this warp inside the segment
+            const int lp = lp0 + lane;
             const uint32_t a = it & 1u;
             mbar_wait(&bar_acc_full[a], (it >> 1) & 1u);
             tc_fence_after();
             const int row = sb * p.pix_per_seg + lp;
             const bool row_ok = lp < p.pix_per_seg && row < p.M;
-            const uint32_t t_lane = tmem_base + a * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
-            size_t spec_base = 0;
-            if (p.spec_nframes > 0 && row_ok) {
-                const int b = row / p.spec_nframes, tt = row - b * p.spec_nframes;
-                spec_base = ((size_t)b * p.cout * p.spec_nframes + tt) * p.spec_nch + p.spec_ch;
-            }
-            for (int c0 = cgrp * 16; c0 < NT; c0 += 16 * (EPI_WARPS / 4)) {
-                float v[16];
-                __syncwarp();                          // tcgen05.ld is .sync.aligned: reconverge first
-                tmem_ld16(t_lane + (uint32_t)c0, v);
-                const int n = n_tile * NT + c0;
-                if (!row_ok || n >= p.cout) continue;
-                if (p.spec_nframes > 0) {
-                    // spectrogram: square, power-compress, scatter (lanes = consecutive frames -> coalesced)
+            const uint32_t t_lane = tmem_base + a * 2u * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
+            if (staged) {
+                for (int c0 = cset * 32; c0 < NT; c0 += 32 * nsets) {
+                    const int gw = NT - c0 < 32 ? 16 : 32;         // NT is a multiple of 16
+                    for (int h = 0; h < gw; h += 16) {
+                        uint32_t rm[16], rc[16];
+                        __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
+                        tmem_ld16_nowait(t_lane + (uint32_t)(c0 + h), rm);
+                        tmem_ld16_nowait(t_lane + (uint32_t)(NT + c0 + h), rc);
+                        tmem_ld_wait();
+                        const int n = n_tile * NT + c0 + h;
+                        float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (n + j >= p.cout) break;
-                        const float pw = v[j] * v[j];
-                        const float r = pw > 0.f ? exp2f(p.spec_exponent * __log2f(pw)) : pw;
-                        const size_t o = spec_base + (size_t)(n + j) * p.spec_nframes * p.spec_nch;
-                        const __half hh = __float2half_rn(r);
-                        p.out_hi[o] = hh;
-                        p.out_hi[p.out_plane + o] = __float2half_rn(r - __half2float(hh));
-                    }
-                    continue;
-                }
-                const size_t o = (size_t)row * p.cout + n;
-                if (vec) {
-                    const float* bs = s_bias_ok ? s_bias + n : nullptr;
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 bv = s_bias_ok ? *reinterpret_cast<const float4*>(s_bias + n + 4 * j4)
+                                                        : __ldg(reinterpret_cast<const float4*>(p.bias + n) + j4);
+                            v[4 * j4 + 0] = __uint_as_float(rm[4 * j4 + 0]) + __uint_as_float(rc[4 * j4 + 0]) + bv.x;
+                            v[4 * j4 + 1] = __uint_as_float(rm[4 * j4 + 1]) + __uint_as_float(rc[4 * j4 + 1]) + bv.y;
+                            v[4 * j4 + 2] = __uint_as_float(rm[4 * j4 + 2]) + __uint_as_float(rc[4 * j4 + 2]) + bv.z;
+                            v[4 * j4 + 3] = __uint_as_float(rm[4 * j4 + 3]) + __uint_as_float(rc[4 * j4 + 3]) + bv.w;
+                        }
+                        if (p.act == KACT_SILU) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += bs ? bs[j] : __ldg(p.bias + n + j);
-                    if (p.act == KACT_SILU) {
+                            for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                        } else if (p.act == KACT_SIGMOID) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
-                    } else if (p.act == KACT_SIGMOID) {
+                            for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+                        }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
-                    }
-                    if (p.res_hi) {
-#pragma unroll
-                        for (int h8 = 0; h8 < 2; ++h8) {
-                            uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + h8);
-                            uint4 rl = __ldg(reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + o) + h8);
-                            float fh[8], fl[8];
-                            unpack8(rh, fh);
-                            unpack8(rl, fl);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[8 * h8 + e] += fh[e] + fl[e];
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int cc = (h >> 2) + j4;          // 16-byte chunk of the 32-column row
+                            *reinterpret_cast<float4*>(stg + lane * 32 + ((cc ^ (lane & 7)) << 2)) =
+                                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
                         }
                     }
-                    if (p.out_f32) {
+                    __syncwarp();
+                    const int osh = gw == 32 ? 2 : 1;              // log2(8-column octets per row)
+                    const int opr = 1 << osh;
+                    const int rpi = 32 >> osh;                     // rows per iteration
+                    const int oc = lane & (opr - 1);
+#pragma unroll 2
+                    for (int i = 0; i < opr; ++i) {
+                        const int r = i * rpi + (lane >> osh);
+                        const float4 x0 = *reinterpret_cast<const float4*>(stg + r * 32 + (((2 * oc) ^ (r & 7)) << 2));
+                        const float4 x1 = *reinterpret_cast<const float4*>(stg + r * 32 + (((2 * oc + 1) ^ (r & 7)) << 2));
+                        const int lpr = lp0 + r;
+                        const int rr = sb * p.pix_per_seg + lpr;
+                        if (lpr < p.pix_per_seg && rr < p.M) {
+                            float w8[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                            const size_t o = (size_t)rr * p.cout + n_tile * NT + c0 + oc * 8;
+                            if (p.res_hi) {
+                                const uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
+                                const uint4 rl = __ldg(reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + o));
+                                float fh[8], fl[8];
+                                unpack8(rh, fh);
+                                unpack8(rl, fl);
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4)
-                            reinterpret_cast<float4*>(p.out_f32 + o)[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                    } else {
-#pragma unroll
-                        for (int h8 = 0; h8 < 2; ++h8) {
+                                for (int e = 0; e < 8; ++e) w8[e] += fh[e] + fl[e];
+                            }
                             uint4 hi, lo;
-                            split8(v + 8 * h8, hi, lo);
-                            reinterpret_cast<uint4*>(p.out_hi + o)[h8] = hi;
-                            reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o)[h8] = lo;
+                            split8(w8, hi, lo);
+                            *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
+                            *reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o) = lo;
                         }
                     }
-                } else {
+                    __syncwarp();                                  // staging tile free for the next group
+                }
+            } else {
+                size_t spec_base = 0;
+                if (p.spec_nframes > 0 && row_ok) {
+                    const int b = row / p.spec_nframes, tt = row - b * p.spec_nframes;
+                    spec_base = ((size_t)b * p.cout * p.spec_nframes + tt) * p.spec_nch + p.spec_ch;
+                }
+                for (int c0 = cset * 16; c0 < NT; c0 += 16 * nsets) {
+                    uint32_t rm[16], rc[16];
+                    float v[16];
+                    __syncwarp();
+                    tmem_ld16_nowait(t_lane + (uint32_t)c0, rm);
+                    tmem_ld16_nowait(t_lane + (uint32_t)(NT + c0), rc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+                    const int n = n_tile * NT + c0;
+                    if (!row_ok || n >= p.cout) continue;
+                    if (p.spec_nframes > 0) {
+                        // spectrogram: square, power-compress, scatter (lanes = consecutive frames -> coalesced)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (n + j >= p.cout) break;
+                            const float pw = v[j] * v[j];
+                            const float r = pw > 0.f ? exp2f(p.spec_exponent * __log2f(pw)) : pw;
+                            const size_t o = spec_base + (size_t)(n + j) * p.spec_nframes * p.spec_nch;
+                            const __half hh = __float2half_rn(r);
+                            p.out_hi[o] = hh;
+                            p.out_hi[p.out_plane + o] = __float2half_rn(r - __half2float(hh));
+                        }
+                        continue;
+                    }
+                    const size_t o = (size_t)row * p.cout + n;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (n + j >= p.cout) break;
-                        float r = act_fn(v[j] + p.bias[n + j], p.act);
+                        float r = act_fn(v[j] + __ldg(p.bias + n + j), p.act);
                         if (p.res_hi) r += __half2float(p.res_hi[o + j]) + __half2float(p.res_hi[p.res_plane + o + j]);
                         if (p.out_f32) {
                             p.out_f32[o + j] = r;
@@ -490,44 +537,52 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     if (warp == 4) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-size_t tc_conv_smem_bytes(int nt, int stages) {
-    return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)nt * 128) + 1024;
+constexpr size_t SMEM_TWO_PER_SM = 108 * 1024;     // dynamic bytes that still let two CTAs share an SM
+constexpr size_t SMEM_ONE_PER_SM = 220 * 1024;
+
+size_t tc_conv_smem_bytes(int nt, int stages, int epi_warps) {
+    return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)nt * 128) + 1024 + (size_t)epi_warps * EPI_STAGE_BYTES;
 }
 
 size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots) {
     const size_t plane = (size_t)(cin / 8) * HALO_PIX * 16;
     const size_t slot = (2 * plane + 1023) & ~(size_t)1023;
-    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024;
+    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024 + (size_t)MAX_EPI_WARPS * EPI_STAGE_BYTES;
 }
 
 int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks) {
     if (k != 3 || stride != 1 || pad != 1 || (cin & 15) || wout != win || (wout % TM) != 0) return 0;
     for (int s = MAX_HALO_SLOTS; s >= 2; --s)
-        if (tc_conv_halo_smem_bytes(cin, nt, k_chunks, s) <= 200 * 1024) return s;
+        if (tc_conv_halo_smem_bytes(cin, nt, k_chunks, s) <= SMEM_ONE_PER_SM) return s;
     return 0;
 }
 
+// two CTAs per SM (4 epilogue warps each, <= 256 TMEM columns each) when at least two stages fit,
+// else one CTA per SM with 8 epilogue warps and the deepest ring that fits
+static bool two_per_sm(int nt, int stages) { return 4 * nt <= 256 && tc_conv_smem_bytes(nt, stages, 4) <= SMEM_TWO_PER_SM; }
+
 int tc_conv_pick_stages(int nt, int k_chunks) {
     (void)k_chunks;                     // the ring runs across tiles, so depth is useful even for K <= 64
-    // prefer two CTAs per SM (<= 104 KB each) when at least two stages fit, else one deep ring
+    if (two_per_sm(nt, 2)) {
+        int s = MAX_STAGES;
+        while (s > 2 && !two_per_sm(nt, s)) --s;
+        return s;
+    }
     int s = MAX_STAGES;
-    while (s > 2 && tc_conv_smem_bytes(nt, s) > 104 * 1024) --s;
-    if (tc_conv_smem_bytes(nt, s) <= 104 * 1024) return s;
-    s = MAX_STAGES;
-    while (s > 2 && tc_conv_smem_bytes(nt, s) > 200 * 1024) --s;
+    while (s > 2 && tc_conv_smem_bytes(nt, s, MAX_EPI_WARPS) > SMEM_ONE_PER_SM) --s;
     return s;
 }
 
 cudaError_t tc_conv_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES_SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES_SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_tc_conv<TC_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    return cudaFuncSetAttribute(k_tc_conv<TC_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
 }
 
 cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t stream) {
@@ -538,8 +593,8 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
     }
     if (p.in_mode == TC_IN_TMA && (p.kb != 16 && p.kb != 32 && p.kb != 64)) return cudaErrorInvalidValue;
     if (p.k_chunks > MAX_K_CHUNKS || p.k * p.k > 31) return cudaErrorInvalidValue;
-    if ((p.cin & 7) || p.nt < 16 || p.nt > 256 || (p.nt & 15) || p.stages < 2 || p.stages > MAX_STAGES ||
-        p.tmem_cols < 2 * p.nt || p.tmem_cols > 512)
+    if ((p.cin & 7) || p.nt < 16 || p.nt > 128 || (p.nt & 15) || p.stages < 2 || p.stages > MAX_STAGES ||
+        p.tmem_cols < 4 * p.nt || p.tmem_cols > 512)
         return cudaErrorInvalidValue;
     const int total = p.m_tiles * p.n_tiles;
     if (p.in_mode == TC_IN_HALO) {
@@ -548,24 +603,26 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
             (p.wout % TM) != 0 || p.win != p.wout || p.K != 9 * p.cin)
             return cudaErrorInvalidValue;
         const size_t hs = tc_conv_halo_smem_bytes(p.cin, p.nt, p.k_chunks, p.stages);
-        if (hs > 208 * 1024) return cudaErrorInvalidValue;
+        if (hs > SMEM_ONE_PER_SM) return cudaErrorInvalidValue;
         int g = total < num_sms ? total : num_sms;
         g -= g % p.n_tiles;
         if (g <= 0) return cudaErrorInvalidValue;
         k_tc_conv<TC_IN_HALO><<<g, NTHREADS, hs, stream>>>(p);
         return cudaGetLastError();
     }
-    size_t smem = tc_conv_smem_bytes(p.nt, p.stages);
     // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
-    const int per_sm = ((p.in_mode == TC_IN_PLANES || p.in_mode == TC_IN_TMA) && smem <= 104 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    const int per_sm = ((p.in_mode == TC_IN_PLANES || p.in_mode == TC_IN_TMA) && two_per_sm(p.nt, p.stages)) ? 2 : 1;
+    const int epi_warps = per_sm == 2 ? 4 : MAX_EPI_WARPS;
+    const size_t smem = tc_conv_smem_bytes(p.nt, p.stages, epi_warps);
+    if (smem > SMEM_ONE_PER_SM) return cudaErrorInvalidValue;
     const int slots = num_sms * per_sm;
     dim3 grid((unsigned)(total < slots ? total : slots));
-    if (smem > 208 * 1024) return cudaErrorInvalidValue;
+    const unsigned nthr = (unsigned)(5 + epi_warps) * 32u;
     switch (p.in_mode) {
-        case TC_IN_PLANES: k_tc_conv<TC_IN_PLANES><<<grid, NTHREADS, smem, stream>>>(p); break;
-        case TC_IN_PLANES_SCALED: k_tc_conv<TC_IN_PLANES_SCALED><<<grid, NTHREADS, smem, stream>>>(p); break;
-        case TC_IN_TMA: k_tc_conv<TC_IN_TMA><<<grid, NTHREADS, smem, stream>>>(p); break;
-        default: k_tc_conv<TC_IN_F32><<<grid, NTHREADS, smem, stream>>>(p); break;
+        case TC_IN_PLANES: k_tc_conv<TC_IN_PLANES><<<grid, nthr, smem, stream>>>(p); break;
+        case TC_IN_PLANES_SCALED: k_tc_conv<TC_IN_PLANES_SCALED><<<grid, nthr, smem, stream>>>(p); break;
+        case TC_IN_TMA: k_tc_conv<TC_IN_TMA><<<grid, nthr, smem, stream>>>(p); break;
+        default: k_tc_conv<TC_IN_F32><<<grid, nthr, smem, stream>>>(p); break;
     }
     return cudaGetLastError();
 }

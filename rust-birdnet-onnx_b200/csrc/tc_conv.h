@@ -57,7 +57,7 @@ struct TcConvParams {
 
 cudaError_t tc_conv_init_device();
 cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stream);
-size_t tc_conv_smem_bytes(int nt, int stages);
+size_t tc_conv_smem_bytes(int nt, int stages, int epi_warps);
 int tc_conv_pick_stages(int nt, int k_chunks);
 // TC_IN_HALO (3x3 stride-1 pad-1 conv, wout % 128 == 0, cin % 16 == 0): weights resident in smem,
 // each input pixel staged ONCE per tile (3 rows x 130 pixels) and the nine taps read as row-shifted
