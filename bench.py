@@ -106,6 +106,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _ncu_traffic():
+    """{stage: DRAM bytes per launch} from the committed ncu --set full capture (profiles/*_ncu_traffic.json,
+    written by tools/ncu_summarize.py); the most recent file by name wins."""
+    d = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(n for n in os.listdir(d) if n.endswith("_ncu_traffic.json"))
+        if not names:
+            return {}, None
+        with open(os.path.join(d, names[-1])) as f:
+            return json.load(f).get("traffic", {}), names[-1]
+    except (OSError, ValueError):
+        return {}, None
+
+
 def _dist():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -330,8 +344,11 @@ def run_ours(args):
         st = [(n, float(np.mean(v))) for n, v in acc.items()]
         dom, stages = _stage_roofline(spec, st, B, peaks)
         if dom:
+            traffic, traffic_src = _ncu_traffic()
             roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
-                    "frac": dom["frac"], "traffic": None, "kernel": dom["stage"], "kernel_ms": dom["ms"],
+                    "frac": dom["frac"], "traffic": traffic.get(dom["stage"]), "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": (dom["alg_per_segment"] * B if dom["bound"] == "hbm" else None),
+                    "kernel": dom["stage"], "kernel_ms": dom["ms"],
                     "share_of_step": dom["share"], "peak_source": peaks["src"] + (" sustained" if dom["bound"] == "tensor" else ""),
                     "algorithmic_per_segment": dom["alg_per_segment"]}
 
@@ -375,7 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--pipeline-depth", type=int, default=4)
+    ap.add_argument("--pipeline-depth", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
