@@ -174,6 +174,12 @@ int bn_ctx_enqueue_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int
 }
 int bn_ctx_wait(bn_ctx* ctx, const bn_run_opts* opts, bn_outputs* out) { return ctx_wait(ctx, opts, out); }
 
+// development aid (not in the public header): role cycle counters of the tensor-core conv launches
+extern "C" int bn_debug_tc_profile(unsigned long long* out, int slots) {
+    cudaError_t e = bn::tc_conv_prof_read(out, slots);
+    return e == cudaSuccess ? BN_OK : bn::cuda_fail(e, "tc_conv_prof_read");
+}
+
 int bn_ctx_read_tensor(bn_ctx* ctx, const char* name, float* dst, uint64_t dst_elems, uint64_t* elems_out) {
     if (!ctx || !name) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
     const Plan& p = ctx->eng->plan;

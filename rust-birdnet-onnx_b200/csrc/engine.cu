@@ -175,6 +175,7 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
     const char* env_tc = getenv("BN_DISABLE_TC");
     const bool tc_enabled = !(env_tc && env_tc[0] == '1');
     e->tc_mode = tc_enabled;
+    { const char* ev = getenv("BN_DISABLE_TMA"); e->use_tma = !(ev && ev[0] == '1'); }
     e->num_sms = prop.multiProcessorCount;
     const char* env_st = getenv("BN_TC_STAGES");
     const int forced_stages = env_st ? atoi(env_st) : 0;
@@ -207,7 +208,6 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             std::vector<uint16_t> pack;
             tc_pack_weights(op.weight.data(), K, op.cout, op.ldw, d.nt, pack, &d.n_tiles, &d.k_chunks);
             d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks);
-            while (d.stages > 2 && tc_conv_smem_bytes(d.nt, d.stages, 8) > 220 * 1024) --d.stages;
             d.tmem_cols = 32;
             while (d.tmem_cols < 4 * d.nt) d.tmem_cols <<= 1;      // 2 buffers x (main | correction)
             BN_CUDA(cudaMalloc(&d.wpack, pack.size() * sizeof(uint16_t)));
@@ -498,6 +498,24 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
                 const bool gated = op.in_scale >= 0 && (int)i != prescaled_conv;
                 tp.in_mode = gated ? TC_IN_PLANES_SCALED : (d.halo_slots > 0 ? TC_IN_HALO : TC_IN_PLANES);
                 tp.in_scale = gated ? c->d_tensor[op.in_scale] : nullptr;
+                // 1x1 stride-1 layers: the A operand is a plain [rows][cin] matrix per plane -> one TMA box per
+                // plane and K chunk lands it in the SWIZZLE_128B layout, no per-thread cp.async address work
+                if (!gated && e->use_tma && op.k == 1 && op.stride == 1 && op.pad == 0 && op.cin <= 256) {   // measured: deep-K projections are faster with the cp.async gather
+                    if (c->tmap_state.empty()) { c->tmaps.resize(p.ops.size()); c->tmap_state.assign(p.ops.size(), 0); }
+                    if (c->tmap_state[i] == 0) {
+                        const uint64_t rows = (uint64_t)std::max<uint64_t>(c->max_batch, 1) * op.hin * op.win;
+                        const uint64_t dims[5] = {(uint64_t)op.cin, rows, 1, 1, 2};
+                        const uint64_t strides[4] = {(uint64_t)op.cin * 2, rows * op.cin * 2, rows * op.cin * 2, (uint64_t)ip.plane * 2};
+                        const uint32_t box[5] = {64, 128, 1, 1, 1};
+                        const uint32_t es[5] = {1, 1, 1, 1, 1};
+                        c->tmap_state[i] = tc_encode_tmap(&c->tmaps[i], ip.hi, dims, strides, box, es, 64) ? 1 : 2;
+                    }
+                    if (c->tmap_state[i] == 1) {
+                        tp.tmap = c->tmaps[i];
+                        tp.in_mode = TC_IN_TMA;
+                        tp.kb = 64; tp.flat = 1;
+                    }
+                }
             } else {
                 tp.in_f32 = c->d_tensor[op.in];
                 tp.in_mode = TC_IN_F32;
@@ -523,7 +541,9 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             tp.M = B * op.hout * op.wout;
             tp.pix_stride = op.cin; tp.seg_stride = op.hin * op.win * op.cin; tp.tab_cin = op.cin;
             tp.k_chunks = d.k_chunks; tp.n_tiles = d.n_tiles; tp.m_tiles = (tp.M + 127) / 128;
+            tp.tiles_per_seg = tp.m_tiles; tp.pix_per_seg = tp.M;
             tp.nt = d.nt; tp.stages = tp.in_mode == TC_IN_HALO ? d.halo_slots : d.stages; tp.tmem_cols = d.tmem_cols;
+            tp.prof = c->profiling && getenv("BN_TC_PROFILE") ? tc_conv_prof_slot((int)i) : nullptr;
             BN_CUDA(launch_tc_conv(tp, e->num_sms, s));
         } else if (is_spatial(p, op.in) || is_spatial(p, op.out)) {
             ConvPlanesParams cp{};

@@ -64,6 +64,7 @@ struct bn_engine {
     int pack_threads = 0;
     bool tc_mode = true;          // tensor-core path with hi/lo-plane activations (BN_DISABLE_TC=1 -> FP32 CUDA-core path)
     int num_sms = 148;
+    bool use_tma = true;          // TMA tile loads for 1x1 layers (BN_DISABLE_TMA=1 -> cp.async gather)
     bn::Plan plan;
     bn_io_info info{};
     std::vector<bn::DevOp> dev_ops;
@@ -97,6 +98,8 @@ struct bn_ctx {
     bool keep_normalized = true;   // write the FP32 normalised audio (tests: BN_KEEP_NORMALIZED=1; always in FP32 mode)
     std::vector<__half*> d_xp;   // per branch: hi/lo planes of the frame matrix [max_batch][rows][row_stride]
     std::vector<float*> d_tensor;   // per plan tensor (aliases resolved to their root)
+    std::vector<CUtensorMap> tmaps;   // per plan op: tensor map of its input planes (TC_IN_TMA layers), encoded on first use
+    std::vector<uint8_t> tmap_state;  // 0 = not tried, 1 = ready, 2 = unavailable
     float* h_logits = nullptr;   // pinned
     float* h_emb = nullptr;      // pinned
     bn::Pred* d_topk = nullptr;

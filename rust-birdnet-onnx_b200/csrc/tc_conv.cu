@@ -17,6 +17,9 @@
 #include "tc_common.cuh"
 #include "tc_conv.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace bn {
 using namespace tc;
 
@@ -30,8 +33,9 @@ constexpr int A_TILE_BYTES = TM * 128;
 constexpr int HALO_W = TM + 2;               // patch columns (one 128-pixel run of an image row + halo)
 constexpr int HALO_PIX = 3 * HALO_W;           // patch pixels: 3 input rows
 constexpr int MAX_HALO_SLOTS = 3;
-constexpr int MAX_EPI_WARPS = 8;     // 8 (one CTA per SM) or 4 (two CTAs per SM): warps 5.. of the CTA
+constexpr int MAX_EPI_WARPS = 16;    // one CTA per SM: 8 or 16 epilogue warps; two CTAs per SM: 4 each (warps 5.. of the CTA)
 constexpr int NTHREADS = (5 + MAX_EPI_WARPS) * 32;
+static int g_epi_warps_one = 16;     // BN_EPI_WARPS=8|16 (development knob)
 
 __device__ __forceinline__ float act_fn(float v, int act) {
     if (act == KACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
@@ -54,8 +58,21 @@ __device__ __forceinline__ void unpack8(const uint4& q, float v[8]) {
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(NTHREADS, (MODE == TC_IN_PLANES || MODE == TC_IN_TMA) ? 2 : 1)
+// ---- development aid: where each role of CTA 0 spends its cycles --------------------------------
+//  [0] producer: wait for a free ring slot   [1] producer: total loop
+//  [2] MMA: wait acc_empty   [3] MMA: wait stage full   [4] MMA: total loop
+//  [5] epilogue warp 5: wait acc_full   [6] epilogue warp 5: total loop   [7] tiles of CTA 0
+__device__ unsigned long long g_tc_prof[128 * 16];
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc, bool on) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
+
+// TWO: built for two co-resident CTAs per SM (288 threads, <= 113 registers) instead of one (up to 672 threads)
+template <int MODE, bool TWO = false>
+__global__ void __launch_bounds__(TWO ? 288 : NTHREADS, TWO ? 2 : 1)
 k_tc_conv(const __grid_constant__ TcConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
@@ -64,13 +81,21 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     __shared__ __align__(8) uint64_t bar_acc_empty[2];
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(8) uint64_t bar_w;         // HALO: resident weights landed
+    __shared__ __align__(8) uint64_t halo_db[18];
+    __shared__ uint32_t halo_a16[18];
     __shared__ uint32_t tap_tab[MAX_K_CHUNKS * 8];   // (element offset << 5) | tap bit
-    __shared__ float s_bias[MAX_SMEM_BIAS];
+    __shared__ __align__(16) float s_bias[MAX_SMEM_BIAS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.nt, STAGES = p.stages;
     const int nthreads = (int)blockDim.x;
     const int epi_warps = (nthreads >> 5) - 5;
+    // narrow tiles (NT <= 32) with 8 epilogue warps: the per-tile epilogue is a latency chain, so the two
+    // warp sets take alternate tiles (accumulator a <-> set a) instead of splitting the few columns
+    const bool tile_split = epi_warps >= 8 && NT <= 32;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0;
+    unsigned long long pw0 = 0, pw1 = 0;
+    const long long prof_t0 = prof ? clock64() : 0;
     const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)NT * 128u;
     const uint32_t w_bytes = 2u * (uint32_t)NT * 128u;
     const int total_tiles = p.m_tiles * p.n_tiles;
@@ -85,7 +110,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         mbar_init(&bar_w, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_acc_full[a], 1);    // tcgen05.commit
-            mbar_init(&bar_acc_empty[a], (uint32_t)epi_warps);   // one arrive per epilogue warp
+            mbar_init(&bar_acc_empty[a], tile_split ? (uint32_t)(epi_warps >> 1) : (uint32_t)epi_warps);   // one arrive per epilogue warp serving it
         }
         fence_barrier_init();
     }
@@ -128,8 +153,23 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 bulk_copy_g2s(tiles + (size_t)kc * w_bytes, src, w_bytes, &bar_w);
             }
         }
+        // The cell -> (smem offset, global offset relative to the tile's first pixel, border flags) map is
+        // the same for every tile: computed once, kept in registers (cin <= 32 -> at most 13 cells / thread).
         const int J = p.cin >> 3;
         const int cells = J * HALO_PIX;                          // 16-byte cells per plane
+        constexpr int HC = 13;
+        uint32_t soff[HC];
+        int32_t goff[HC];
+        uint32_t flg[HC];                                        // 1: row 0, 2: row 2, 4: col 0, 8: last col, 16: no cell
+#pragma unroll
+        for (int i = 0; i < HC; ++i) {
+            const int e = tid + 128 * i;
+            const int pix = e / J, j = e - pix * J;              // consecutive lanes: the J cells of a pixel, then the next pixel
+            const int r = pix / HALO_W, x = pix - r * HALO_W;
+            soff[i] = (uint32_t)(j * HALO_PIX + pix) * 16u;
+            goff[i] = ((r - 1) * p.win + (x - 1)) * p.cin + j * 8;
+            flg[i] = (r == 0 ? 1u : 0u) | (r == 2 ? 2u : 0u) | (x == 0 ? 4u : 0u) | (x == HALO_W - 1 ? 8u : 0u) | (e >= cells ? 16u : 0u);
+        }
         const __half* in_lo = p.in_hi + p.in_plane;
         const int hw = p.hout * p.wout;
         uint32_t s = 0, ph = 0;
@@ -137,24 +177,26 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const int m0 = (t / p.n_tiles) * TM;
             const int b = m0 / hw, rem = m0 - b * hw;
             const int oy = rem / p.wout, ox0 = rem - oy * p.wout;
-            mbar_wait(&bar_empty[s], ph ^ 1u);
+            const uint32_t bad = (oy == 0 ? 1u : 0u) | (oy == p.hin - 1 ? 2u : 0u) | (ox0 == 0 ? 4u : 0u) |
+                                 (ox0 + TM == p.win ? 8u : 0u) | 16u;
+            const int tile_base = b * p.seg_stride + (oy * p.win + ox0) * p.cin;
+            mbar_wait_t(&bar_empty[s], ph ^ 1u, pw0, prof);
             const uint32_t d0 = smem_u32(halo_slots + (size_t)s * halo_slot_bytes);
-            const int seg_base = b * p.seg_stride;
-            for (int e = tid; e < cells; e += 128) {
-                const int pix = e / J, j = e - pix * J;          // consecutive lanes: the J cells of a pixel, then the next pixel
-                const int r = pix / HALO_W, x = pix - r * HALO_W;
-                const int iy = oy - 1 + r, ix = ox0 - 1 + x;
-                const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.win;
-                const int eo = ok ? seg_base + (iy * p.win + ix) * p.cin + j * 8 : 0;
+#pragma unroll
+            for (int i = 0; i < HC; ++i) {
+                const bool ok = (flg[i] & bad) == 0u;
+                const int eo = ok ? tile_base + goff[i] : 0;     // masked cells never form an address
                 const uint32_t nb = ok ? 16u : 0u;
-                const uint32_t d = d0 + (uint32_t)(j * HALO_PIX + pix) * 16u;
-                cp_async16(d, p.in_hi + eo, nb);
-                cp_async16(d + halo_plane_bytes, in_lo + eo, nb);
+                if ((flg[i] & 16u) == 0u) {
+                    cp_async16(d0 + soff[i], p.in_hi + eo, nb);
+                    cp_async16(d0 + soff[i] + halo_plane_bytes, in_lo + eo, nb);
+                }
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
             if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
         }
         cp_async_wait_all();
+        if (prof && tid == 0) { p.prof[0] = pw0; p.prof[1] = (unsigned long long)(clock64() - prof_t0); }
     } else if (MODE == TC_IN_TMA && warp < 4) {
         // ================================ TMA producer (one thread) ================================
         if (tid == 0) {
@@ -244,7 +286,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 }
             }
             for (int kc = 0; kc < p.k_chunks; ++kc) {
-                mbar_wait(&bar_empty[s], ph ^ 1u);
+                mbar_wait_t(&bar_empty[s], ph ^ 1u, pw0, prof);
                 uint8_t* st = tiles + (size_t)s * stage_bytes;
                 if (tid == 0) {
                     asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
@@ -311,6 +353,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             }
         }
         if (MODE == TC_IN_PLANES) cp_async_wait_all();   // nothing may be in flight when the CTA exits
+        if (prof && tid == 0) { p.prof[0] = pw0; p.prof[1] = (unsigned long long)(clock64() - prof_t0); }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
         // Accumulator a = TMEM columns [a*2NT, a*2NT + 2NT): [main = A_hi*W_hi | corr = A_hi*W_lo + A_lo*W_hi].
@@ -318,75 +361,93 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         // correction terms out of the big accumulator cuts the number of truncating adds 3x and the
         // epilogue adds main + corr once, round-to-nearest.  W_hi and W_lo tiles are adjacent in smem,
         // so A_hi * [W_hi | W_lo] is ONE MMA of N = 2NT.
-        if (MODE == TC_IN_HALO && lane == 0) {
-            const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
-            const uint32_t lbo = HALO_PIX * 16u;                 // next 8-channel group of the same pixels
+        if (MODE == TC_IN_HALO) {
+            // per K step (tap, 16 channels): A start-address delta and the B descriptor; tile-invariant
             const int ksteps = p.cin >> 4;
+            const int nsteps = 9 * ksteps;                       // <= 18 (cin <= 32)
+            const uint32_t lbo = HALO_PIX * 16u;                 // next 8-channel group of the same pixels
+            for (int i = lane; i < nsteps; i += 32) {
+                const int tap = i / ksteps, ks = i - tap * ksteps;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const int k = tap * p.cin + ks * 16;
+                halo_a16[i] = ((uint32_t)(2 * ks) * lbo + (uint32_t)(ky * HALO_W + kx) * 16u) >> 4;   // row m <-> patch pixel m + ky*130 + kx
+                halo_db[i] = umma_desc_sw128(smem_u32(tiles) + (uint32_t)(k >> 6) * w_bytes) + (uint64_t)(kDescKStep * ((k & 63) >> 4));
+            }
+            __syncwarp();
+          if (lane == 0) {
+            const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
+            const uint64_t lo_delta = (uint64_t)(halo_plane_bytes >> 4);
             mbar_wait(&bar_w, 0);
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const uint32_t a = it & 1u;
-                mbar_wait(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u);
-                mbar_wait(&bar_full[s], ph);
+                mbar_wait_t(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u, pw0, prof);
+                mbar_wait_t(&bar_full[s], ph, pw1, prof);
                 fence_proxy_async_smem();
                 tc_fence_after();
                 const uint32_t acc = tmem_base + a * 2u * (uint32_t)NT;
-                const uint32_t a_hi = smem_u32(halo_slots + (size_t)s * halo_slot_bytes);
-                const uint32_t w0 = smem_u32(tiles);
-                uint32_t first = 0;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const uint32_t shift = (uint32_t)(ky * HALO_W + kx) * 16u;      // row m <-> patch pixel m + ky*130 + kx
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const int k = tap * p.cin + ks * 16;
-                        const uint32_t wb = w0 + (uint32_t)(k >> 6) * w_bytes;
-                        const uint64_t adv = (uint64_t)(kDescKStep * ((k & 63) >> 4));
-                        const uint64_t db_hi = umma_desc_sw128(wb) + adv;
-                        const uint32_t a_off = (uint32_t)(2 * ks) * lbo + shift;
-                        const uint64_t da_hi = umma_desc_nosw(a_hi + a_off, lbo, 128u);
-                        const uint64_t da_lo = umma_desc_nosw(a_hi + halo_plane_bytes + a_off, lbo, 128u);
-                        umma_f16(acc, da_hi, db_hi, idesc2, first);
-                        umma_f16(acc + (uint32_t)NT, da_lo, db_hi, idesc1, 1u);
-                        first = 1u;
-                    }
+                const uint64_t da0 = umma_desc_nosw(smem_u32(halo_slots + (size_t)s * halo_slot_bytes), lbo, 128u);
+#pragma unroll 6
+                for (int i = 0; i < nsteps; ++i) {
+                    const uint64_t da_hi = da0 + (uint64_t)halo_a16[i];
+                    const uint64_t db = halo_db[i];
+                    umma_f16(acc, da_hi, db, idesc2, i > 0 ? 1u : 0u);
+                    umma_f16(acc + (uint32_t)NT, da_hi + lo_delta, db, idesc1, 1u);
                 }
                 umma_commit(&bar_empty[s]);
                 umma_commit(&bar_acc_full[a]);
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
             }
+            if (prof) { p.prof[2] = pw0; p.prof[3] = pw1; p.prof[4] = (unsigned long long)(clock64() - prof_t0); p.prof[7] = it; }
+          }
         } else if (MODE != TC_IN_HALO && lane == 0) {
             const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const uint32_t a = it & 1u;
-                mbar_wait(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u);
+                mbar_wait_t(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u, pw0, prof);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + a * 2u * (uint32_t)NT;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
-                    mbar_wait(&bar_full[s], ph);
+                    mbar_wait_t(&bar_full[s], ph, pw1, prof);
                     fence_proxy_async_smem();          // cp.async / st.shared (generic proxy) -> tcgen05 reads (async proxy)
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(tiles + (size_t)s * stage_bytes);
                     const uint64_t db_hi = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES);   // [W_hi | W_lo]: 2NT rows
                     int ksteps = (p.K - kc * KC + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
-                    for (int j = 0; j < ksteps; ++j) {
-                        // A: K block of kb channels per sub-tile (kb = 64 -> one SWIZZLE_128B tile per chunk)
-                        const uint32_t kk = (uint32_t)j * 16u;
-                        const uint32_t sub = kk / a_kb, in_sub = kk - sub * a_kb;
-                        const uint32_t a_off = sub * (uint32_t)TM * a_kb * 2u;
-                        const uint64_t da_hi = umma_desc_kmajor(a_hi + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
-                        const uint64_t da_lo = umma_desc_kmajor(a_hi + A_TILE_BYTES + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
-                        const uint64_t adv = (uint64_t)(kDescKStep * j);
-                        umma_f16(acc, da_hi, db_hi + adv, idesc2, (kc | j) != 0 ? 1u : 0u);
-                        umma_f16(acc + (uint32_t)NT, da_lo, db_hi + adv, idesc1, 1u);
+                    if (MODE != TC_IN_TMA) {
+                        // one SWIZZLE_128B [128][64] tile per plane: K step j = +2 in the start-address field
+                        const uint64_t da_hi = umma_desc_sw128(a_hi);
+                        const uint64_t da_lo = da_hi + (uint64_t)(A_TILE_BYTES >> 4);
+                        uint32_t accum = kc != 0 ? 1u : 0u;
+#pragma unroll 4
+                        for (int j = 0; j < ksteps; ++j) {
+                            const uint64_t adv = (uint64_t)(kDescKStep * j);
+                            umma_f16(acc, da_hi + adv, db_hi + adv, idesc2, accum);
+                            umma_f16(acc + (uint32_t)NT, da_lo + adv, db_hi + adv, idesc1, 1u);
+                            accum = 1u;
+                        }
+                    } else {
+                        for (int j = 0; j < ksteps; ++j) {
+                            // A: K block of kb channels per sub-tile (kb = 64 -> one SWIZZLE_128B tile per chunk)
+                            const uint32_t kk = (uint32_t)j * 16u;
+                            const uint32_t sub = kk / a_kb, in_sub = kk - sub * a_kb;
+                            const uint32_t a_off = sub * (uint32_t)TM * a_kb * 2u;
+                            const uint64_t da_hi = umma_desc_kmajor(a_hi + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
+                            const uint64_t da_lo = umma_desc_kmajor(a_hi + A_TILE_BYTES + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
+                            const uint64_t adv = (uint64_t)(kDescKStep * j);
+                            umma_f16(acc, da_hi, db_hi + adv, idesc2, (kc | j) != 0 ? 1u : 0u);
+                            umma_f16(acc + (uint32_t)NT, da_lo, db_hi + adv, idesc1, 1u);
+                        }
                     }
                     umma_commit(&bar_empty[s]);        // frees the smem stage when these MMAs retire
                     if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(&bar_acc_full[a]);         // accumulator complete -> epilogue
             }
+            if (prof) { p.prof[2] = pw0; p.prof[3] = pw1; p.prof[4] = (unsigned long long)(clock64() - prof_t0); p.prof[7] = it; }
         }
         __syncwarp();
     } else {
@@ -397,7 +458,11 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         // whole 32/64-byte row pieces (full sectors) instead of one 16-byte piece in each of 32 lines.
         const int ew = warp - 5;
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int cset = ew >> 2, nsets = epi_warps >> 2;
+        // tile_split: half of the warp sets serve accumulator 0, the other half accumulator 1
+        const int nset_all = epi_warps >> 2;
+        const int wset = tile_split ? (ew >> 2) / (nset_all >> 1) : 0;
+        const int cset = tile_split ? (ew >> 2) % (nset_all >> 1) : (ew >> 2);
+        const int nsets = tile_split ? (nset_all >> 1) : nset_all;
         float* stg = reinterpret_cast<float*>(tiles + ring_bytes + (size_t)ew * EPI_STAGE_BYTES);
         uint32_t it = 0;
         const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
@@ -409,7 +474,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const int lp0 = lt * TM + q * 32;                  // first row of this warp inside the segment
             const int lp = lp0 + lane;
             const uint32_t a = it & 1u;
-            mbar_wait(&bar_acc_full[a], (it >> 1) & 1u);
+            if (tile_split && (int)a != wset) continue;
+            mbar_wait_t(&bar_acc_full[a], (it >> 1) & 1u, pw0, prof && warp == 5);
             tc_fence_after();
             const int row = sb * p.pix_per_seg + lp;
             const bool row_ok = lp < p.pix_per_seg && row < p.M;
@@ -531,6 +597,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[a]);
         }
+        if (prof && warp == 5 && lane == 0) { p.prof[5] = pw0; p.prof[6] = (unsigned long long)(clock64() - prof_t0); }
     }
     tc_fence_before();
     __syncthreads();
@@ -544,14 +611,24 @@ size_t tc_conv_smem_bytes(int nt, int stages, int epi_warps) {
     return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)nt * 128) + 1024 + (size_t)epi_warps * EPI_STAGE_BYTES;
 }
 
+unsigned long long* tc_conv_prof_slot(int slot) {
+    if (slot < 0 || slot >= 128) return nullptr;
+    void* base = nullptr;
+    if (cudaGetSymbolAddress(&base, g_tc_prof) != cudaSuccess) return nullptr;
+    return reinterpret_cast<unsigned long long*>(base) + (size_t)slot * 16;
+}
+cudaError_t tc_conv_prof_read(unsigned long long* out, int slots) {
+    return cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 16 * (size_t)(slots < 128 ? slots : 128));
+}
+
 size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots) {
     const size_t plane = (size_t)(cin / 8) * HALO_PIX * 16;
     const size_t slot = (2 * plane + 1023) & ~(size_t)1023;
-    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024 + (size_t)MAX_EPI_WARPS * EPI_STAGE_BYTES;
+    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024 + (size_t)g_epi_warps_one * EPI_STAGE_BYTES;
 }
 
 int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks) {
-    if (k != 3 || stride != 1 || pad != 1 || (cin & 15) || wout != win || (wout % TM) != 0) return 0;
+    if (k != 3 || stride != 1 || pad != 1 || (cin != 16 && cin != 32) || wout != win || (wout % TM) != 0) return 0;
     for (int s = MAX_HALO_SLOTS; s >= 2; --s)
         if (tc_conv_halo_smem_bytes(cin, nt, k_chunks, s) <= SMEM_ONE_PER_SM) return s;
     return 0;
@@ -569,12 +646,15 @@ int tc_conv_pick_stages(int nt, int k_chunks) {
         return s;
     }
     int s = MAX_STAGES;
-    while (s > 2 && tc_conv_smem_bytes(nt, s, MAX_EPI_WARPS) > SMEM_ONE_PER_SM) --s;
+    while (s > 2 && tc_conv_smem_bytes(nt, s, g_epi_warps_one) > SMEM_ONE_PER_SM) --s;
     return s;
 }
 
 cudaError_t tc_conv_init_device() {
+    { const char* ev = getenv("BN_EPI_WARPS"); if (ev && atoi(ev) == 8) g_epi_warps_one = 8; }
     cudaError_t e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TWO_PER_SM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES_SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
@@ -599,7 +679,7 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
     const int total = p.m_tiles * p.n_tiles;
     if (p.in_mode == TC_IN_HALO) {
         // p.stages = patch slots (tc_conv_halo_slots); every CTA keeps one n tile's weights resident
-        if (p.stages < 2 || p.stages > MAX_HALO_SLOTS || p.k != 3 || p.stride != 1 || p.pad != 1 || (p.cin & 15) ||
+        if (p.stages < 2 || p.stages > MAX_HALO_SLOTS || p.k != 3 || p.stride != 1 || p.pad != 1 || (p.cin != 16 && p.cin != 32) ||
             (p.wout % TM) != 0 || p.win != p.wout || p.K != 9 * p.cin)
             return cudaErrorInvalidValue;
         const size_t hs = tc_conv_halo_smem_bytes(p.cin, p.nt, p.k_chunks, p.stages);
@@ -607,19 +687,22 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
         int g = total < num_sms ? total : num_sms;
         g -= g % p.n_tiles;
         if (g <= 0) return cudaErrorInvalidValue;
-        k_tc_conv<TC_IN_HALO><<<g, NTHREADS, hs, stream>>>(p);
+        k_tc_conv<TC_IN_HALO><<<g, (unsigned)(5 + g_epi_warps_one) * 32u, hs, stream>>>(p);
         return cudaGetLastError();
     }
     // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
-    const int per_sm = ((p.in_mode == TC_IN_PLANES || p.in_mode == TC_IN_TMA) && two_per_sm(p.nt, p.stages)) ? 2 : 1;
-    const int epi_warps = per_sm == 2 ? 4 : MAX_EPI_WARPS;
+    const int per_sm = (p.in_mode == TC_IN_PLANES && two_per_sm(p.nt, p.stages)) ? 2 : 1;
+    const int epi_warps = per_sm == 2 ? 4 : g_epi_warps_one;
     const size_t smem = tc_conv_smem_bytes(p.nt, p.stages, epi_warps);
     if (smem > SMEM_ONE_PER_SM) return cudaErrorInvalidValue;
     const int slots = num_sms * per_sm;
     dim3 grid((unsigned)(total < slots ? total : slots));
     const unsigned nthr = (unsigned)(5 + epi_warps) * 32u;
     switch (p.in_mode) {
-        case TC_IN_PLANES: k_tc_conv<TC_IN_PLANES><<<grid, nthr, smem, stream>>>(p); break;
+        case TC_IN_PLANES:
+            if (per_sm == 2) k_tc_conv<TC_IN_PLANES, true><<<grid, nthr, smem, stream>>>(p);
+            else k_tc_conv<TC_IN_PLANES><<<grid, nthr, smem, stream>>>(p);
+            break;
         case TC_IN_PLANES_SCALED: k_tc_conv<TC_IN_PLANES_SCALED><<<grid, nthr, smem, stream>>>(p); break;
         case TC_IN_TMA: k_tc_conv<TC_IN_TMA><<<grid, nthr, smem, stream>>>(p); break;
         default: k_tc_conv<TC_IN_F32><<<grid, nthr, smem, stream>>>(p); break;
@@ -636,7 +719,11 @@ bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], 
     if (!fn) {
         void* sym = nullptr;
         cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) != cudaSuccess || !sym) return false;
+        cudaError_t ge = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr);
+        if (ge != cudaSuccess || !sym) {
+            if (getenv("BN_DEBUG")) fprintf(stderr, "[bn] cuTensorMapEncodeTiled entry point unavailable: %s (qr=%d)\n", cudaGetErrorString(ge), (int)qr);
+            return false;
+        }
         fn = reinterpret_cast<EncodeFn>(sym);
     }
     const CUtensorMapSwizzle sw = kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -646,6 +733,10 @@ bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], 
     for (int i = 0; i < 4; ++i) gs[i] = strides_bytes[i];
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("BN_DEBUG"))
+        fprintf(stderr, "[bn] cuTensorMapEncodeTiled failed: CUresult %d (dims %llu %llu %llu %llu %llu, strides %llu %llu %llu %llu)\n", (int)r,
+                (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2], (unsigned long long)gd[3], (unsigned long long)gd[4],
+                (unsigned long long)gs[0], (unsigned long long)gs[1], (unsigned long long)gs[2], (unsigned long long)gs[3]);
     return r == CUDA_SUCCESS;
 }
 

@@ -50,12 +50,16 @@ struct TcConvParams {
     int pix_stride;          // elements between consecutive input pixels (= cin for a conv)
     int seg_stride;          // elements between consecutive segments of the input
     int tab_cin;             // channel count used to split K into (tap, channel) (= cin for a conv)
+    unsigned long long* prof;   // optional [16] cycle counters written by CTA 0 (tools/tc_role_profile.py), or nullptr
     int nt;                  // UMMA N of this layer (multiple of 16, <= 256)
     int stages;              // smem ring depth
     int tmem_cols;           // power of two >= max(32, 2 * nt): two accumulators
 };
 
 cudaError_t tc_conv_init_device();
+// development aid: per-launch role wait-cycle counters (slot < 128, 16 counters each); see tc_conv.cu
+unsigned long long* tc_conv_prof_slot(int slot);
+cudaError_t tc_conv_prof_read(unsigned long long* out, int slots);
 cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stream);
 size_t tc_conv_smem_bytes(int nt, int stages, int epi_warps);
 int tc_conv_pick_stages(int nt, int k_chunks);
