@@ -180,6 +180,13 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
     const char* env_st = getenv("BN_TC_STAGES");
     const int forced_stages = env_st ? atoi(env_st) : 0;
 
+    // measured (profiles/r01_stage_times_b256.txt): wide 3x3 tiles (N >= 64) run faster with 8 epilogue warps and a
+    // deeper operand ring, everything else with 16
+    const char* env_epi = getenv("BN_EPI_WARPS");
+    auto epi_rule = [&](int k, int nt) -> int {
+        if (env_epi) return atoi(env_epi);
+        return (k == 3 && nt >= 64) ? 8 : 16;
+    };
     Plan& p = e->plan;
     e->dev_ops.resize(p.ops.size());
     for (size_t i = 0; i < p.ops.size(); ++i) {
@@ -201,13 +208,14 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
                 const int c16 = (op.cout + 15) / 16 * 16;
                 for (int nt = d.nt; nt >= 16; nt -= 16) {
                     if (c16 % nt) continue;
-                    const int slots = tc_conv_halo_slots(op.k, op.stride, op.pad, op.cin, op.wout, op.win, nt, (K + 63) / 64);
+                    const int slots = tc_conv_halo_slots(op.k, op.stride, op.pad, op.cin, op.wout, op.win, nt, (K + 63) / 64, epi_rule(op.k, nt));
                     if (slots >= 2) { d.nt = nt; d.halo_slots = slots; break; }
                 }
             }
+            d.epi_warps = epi_rule(op.k, d.nt);
             std::vector<uint16_t> pack;
             tc_pack_weights(op.weight.data(), K, op.cout, op.ldw, d.nt, pack, &d.n_tiles, &d.k_chunks);
-            d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks);
+            d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks, d.epi_warps);
             d.tmem_cols = 32;
             while (d.tmem_cols < 4 * d.nt) d.tmem_cols <<= 1;      // 2 buffers x (main | correction)
             BN_CUDA(cudaMalloc(&d.wpack, pack.size() * sizeof(uint16_t)));
@@ -460,6 +468,15 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
                 const PlanOp& f2 = p.ops[i + 1];
                 const TensorInfo& dt = p.tensors[p.ops[cv].in];
                 prof_mark(c, op.name.c_str());
+                if (op.cout <= 256) {                        // gate kernel + streaming rescale
+                    BN_CUDA(launch_se_gate(c->d_tensor[op.in], d.weight, d.bias, e->dev_ops[i + 1].weight, e->dev_ops[i + 1].bias,
+                                           c->d_tensor[f2.out], B, dt.C, op.cout, op.ldw, f2.ldw, s));
+                    BN_CUDA(launch_se_rescale(planes_of(c, p.ops[cv].in), c->d_tensor[f2.out], B, dt.H * dt.W, dt.C, s));
+                    launches += 2;
+                    prescaled_conv = cv;
+                    ++i;
+                    continue;
+                }
                 SeParams sp{};
                 sp.pooled = c->d_tensor[op.in];
                 sp.w1 = d.weight; sp.b1 = d.bias; sp.ldw1 = op.ldw;
@@ -543,6 +560,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             tp.k_chunks = d.k_chunks; tp.n_tiles = d.n_tiles; tp.m_tiles = (tp.M + 127) / 128;
             tp.tiles_per_seg = tp.m_tiles; tp.pix_per_seg = tp.M;
             tp.nt = d.nt; tp.stages = tp.in_mode == TC_IN_HALO ? d.halo_slots : d.stages; tp.tmem_cols = d.tmem_cols;
+            tp.epi_warps = d.epi_warps;
             tp.prof = c->profiling && getenv("BN_TC_PROFILE") ? tc_conv_prof_slot((int)i) : nullptr;
             BN_CUDA(launch_tc_conv(tp, e->num_sms, s));
         } else if (is_spatial(p, op.in) || is_spatial(p, op.out)) {

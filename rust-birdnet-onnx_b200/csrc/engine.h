@@ -39,6 +39,7 @@ struct DevOp {
     void* wpack = nullptr;
     int nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32;
     int halo_slots = 0;          // > 0: TC_IN_HALO (patch staged once, taps as shifted views)
+    int epi_warps = 0;           // epilogue warps when the layer runs one CTA per SM (measured per layer class)
 };
 
 struct RangeDev {   // dense per-class tri-state on the device

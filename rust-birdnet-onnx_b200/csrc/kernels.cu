@@ -779,6 +779,112 @@ cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Squeeze-excite gate: gate[b][c] = sigmoid(W2^T silu(W1^T pooled[b] + b1) + b2); one CTA per segment.
+// Pure L2 latency (two dependent FCs over ~150-450 KB of weights), so every load loop keeps 8
+// independent loads in flight.
+__global__ void __launch_bounds__(256) k_se_gate(const float* __restrict__ pooled, const float* __restrict__ w1,
+                                                 const float* __restrict__ b1, const float* __restrict__ w2,
+                                                 const float* __restrict__ b2, float* __restrict__ gate,
+                                                 int c, int r, int ldw1, int ldw2) {
+    extern __shared__ float s_g[];                          // pooled[C] | r[R] | partial[8][R]
+    float* s_p = s_g;
+    float* s_r = s_p + c;
+    float* s_pt = s_r + r;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < c; i += 256) s_p[i] = pooled[(size_t)b * c + i];
+    __syncthreads();
+    const int cpw = (c + 7) / 8;                            // FC1: warps split C, lanes = output j
+    const int cbeg = warp * cpw, cend = min(c, cbeg + cpw);
+    for (int j0 = 0; j0 < r; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < r) {
+            float acc = 0.f;
+            int cc = cbeg;
+            for (; cc + 8 <= cend; cc += 8) {
+                float w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = __ldg(w1 + (size_t)(cc + u) * ldw1 + j);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = fmaf(s_p[cc + u], w[u], acc);
+            }
+            for (; cc < cend; ++cc) acc = fmaf(s_p[cc], __ldg(w1 + (size_t)cc * ldw1 + j), acc);
+            s_pt[warp * r + j] = acc;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < r; j += 256) {
+        float v = b1[j];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_pt[w * r + j];
+        s_r[j] = v * (1.0f / (1.0f + expf(-v)));
+    }
+    __syncthreads();
+    for (int cc = tid; cc < c; cc += 256) {                 // FC2: thread per channel, rows of W2 contiguous in c
+        float v = b2[cc];
+        int j = 0;
+        for (; j + 8 <= r; j += 8) {
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = __ldg(w2 + (size_t)(j + u) * ldw2 + cc);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v = fmaf(s_r[j + u], w[u], v);
+        }
+        for (; j < r; ++j) v = fmaf(s_r[j], __ldg(w2 + (size_t)j * ldw2 + cc), v);
+        gate[(size_t)b * c + cc] = 1.0f / (1.0f + expf(-v));
+    }
+}
+
+cudaError_t launch_se_gate(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* gate, int batch, int c, int r, int ldw1, int ldw2, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    if (r > 256) return cudaErrorInvalidValue;
+    const size_t smem = ((size_t)c + r + 8 * r) * sizeof(float);
+    k_se_gate<<<batch, 256, smem, stream>>>(pooled, w1, b1, w2, b2, gate, c, r, ldw1, ldw2);
+    return cudaGetLastError();
+}
+
+// Pure streaming squeeze-excite rescale: d[b][pix][c] *= gate[b][c], hi/lo planes in place.
+__global__ void __launch_bounds__(256) k_se_rescale(__half* __restrict__ d, size_t plane, const float* __restrict__ gate,
+                                                    int c, unsigned ups, unsigned long long total) {
+    const unsigned upp = (unsigned)c >> 3;                  // 16-byte units per pixel
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256ull;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * 256ull + threadIdx.x; u < total; u += stride) {
+        const unsigned b = (unsigned)(u / ups);
+        const unsigned cu = ((unsigned)(u % upp)) << 3;
+        __half* ph = d + u * 8ull;
+        const uint4 qh = *reinterpret_cast<const uint4*>(ph);
+        const uint4 ql = *reinterpret_cast<const uint4*>(ph + plane);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * c + cu));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * c + cu) + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const __half2* h = reinterpret_cast<const __half2*>(&qh);
+        const __half2* l = reinterpret_cast<const __half2*>(&ql);
+        __half2 oh[4], ol[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 a = __half22float2(h[i]), e = __half22float2(l[i]);
+            const float v0 = (a.x + e.x) * g[2 * i], v1 = (a.y + e.y) * g[2 * i + 1];
+            oh[i] = __floats2half2_rn(v0, v1);
+            const float2 bk = __half22float2(oh[i]);
+            ol[i] = __floats2half2_rn(v0 - bk.x, v1 - bk.y);
+        }
+        *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<uint4*>(oh);
+        *reinterpret_cast<uint4*>(ph + plane) = *reinterpret_cast<uint4*>(ol);
+    }
+}
+
+cudaError_t launch_se_rescale(PlanesPtr d, const float* gate, int batch, int npix, int c, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    if (c & 7) return cudaErrorInvalidValue;
+    const unsigned ups = (unsigned)npix * (unsigned)(c >> 3);
+    const unsigned long long total = (unsigned long long)batch * ups;
+    unsigned long long blocks = (total + 1023) / 1024;       // ~4 units per thread
+    if (blocks > 148ull * 32) blocks = 148ull * 32;
+    if (blocks < 1) blocks = 1;
+    k_se_rescale<<<(unsigned)blocks, 256, 0, stream>>>(d.hi, d.plane, gate, c, ups, total);
+    return cudaGetLastError();
+}
+
 // ======================================================================================
 // Stem: direct k x k conv for tiny Cin (the 2-channel spectrogram), planes in / planes out.
 // One thread per output pixel computes all Cout (<= 32) channels; weights live in smem.

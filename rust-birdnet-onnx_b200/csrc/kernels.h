@@ -106,6 +106,11 @@ struct SeParams {
     int c, r, ldw1, ldw2, npix;
 };
 cudaError_t launch_se_scale(const SeParams& p, int batch, cudaStream_t stream);
+// squeeze-excite as two launches: the gate (one CTA per segment, both FCs) and a pure streaming in-place
+// rescale d[b][pix][c] *= gate[b][c] on the hi/lo planes
+cudaError_t launch_se_gate(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* gate, int batch, int c, int r, int ldw1, int ldw2, cudaStream_t stream);
+cudaError_t launch_se_rescale(PlanesPtr d, const float* gate, int batch, int npix, int c, cudaStream_t stream);
 
 // ---- log-mel front-end (row A9: BirdNET v3.0 / Perch v2), frontend_logmel.cu -------------------
 struct LogmelParams {

@@ -621,16 +621,18 @@ cudaError_t tc_conv_prof_read(unsigned long long* out, int slots) {
     return cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 16 * (size_t)(slots < 128 ? slots : 128));
 }
 
-size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots) {
+static int resolve_epi_warps(int epi_warps) { return epi_warps == 8 || epi_warps == 16 ? epi_warps : g_epi_warps_one; }
+
+size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots, int epi_warps) {
     const size_t plane = (size_t)(cin / 8) * HALO_PIX * 16;
     const size_t slot = (2 * plane + 1023) & ~(size_t)1023;
-    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024 + (size_t)g_epi_warps_one * EPI_STAGE_BYTES;
+    return (size_t)k_chunks * 2 * nt * 128 + (size_t)slots * slot + 1024 + (size_t)resolve_epi_warps(epi_warps) * EPI_STAGE_BYTES;
 }
 
-int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks) {
+int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks, int epi_warps) {
     if (k != 3 || stride != 1 || pad != 1 || (cin != 16 && cin != 32) || wout != win || (wout % TM) != 0) return 0;
     for (int s = MAX_HALO_SLOTS; s >= 2; --s)
-        if (tc_conv_halo_smem_bytes(cin, nt, k_chunks, s) <= SMEM_ONE_PER_SM) return s;
+        if (tc_conv_halo_smem_bytes(cin, nt, k_chunks, s, epi_warps) <= SMEM_ONE_PER_SM) return s;
     return 0;
 }
 
@@ -638,7 +640,7 @@ int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, i
 // else one CTA per SM with 8 epilogue warps and the deepest ring that fits
 static bool two_per_sm(int nt, int stages) { return 4 * nt <= 256 && tc_conv_smem_bytes(nt, stages, 4) <= SMEM_TWO_PER_SM; }
 
-int tc_conv_pick_stages(int nt, int k_chunks) {
+int tc_conv_pick_stages(int nt, int k_chunks, int epi_warps) {
     (void)k_chunks;                     // the ring runs across tiles, so depth is useful even for K <= 64
     if (two_per_sm(nt, 2)) {
         int s = MAX_STAGES;
@@ -646,7 +648,7 @@ int tc_conv_pick_stages(int nt, int k_chunks) {
         return s;
     }
     int s = MAX_STAGES;
-    while (s > 2 && tc_conv_smem_bytes(nt, s, g_epi_warps_one) > SMEM_ONE_PER_SM) --s;
+    while (s > 2 && tc_conv_smem_bytes(nt, s, resolve_epi_warps(epi_warps)) > SMEM_ONE_PER_SM) --s;
     return s;
 }
 
@@ -682,17 +684,17 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
         if (p.stages < 2 || p.stages > MAX_HALO_SLOTS || p.k != 3 || p.stride != 1 || p.pad != 1 || (p.cin != 16 && p.cin != 32) ||
             (p.wout % TM) != 0 || p.win != p.wout || p.K != 9 * p.cin)
             return cudaErrorInvalidValue;
-        const size_t hs = tc_conv_halo_smem_bytes(p.cin, p.nt, p.k_chunks, p.stages);
+        const size_t hs = tc_conv_halo_smem_bytes(p.cin, p.nt, p.k_chunks, p.stages, p.epi_warps);
         if (hs > SMEM_ONE_PER_SM) return cudaErrorInvalidValue;
         int g = total < num_sms ? total : num_sms;
         g -= g % p.n_tiles;
         if (g <= 0) return cudaErrorInvalidValue;
-        k_tc_conv<TC_IN_HALO><<<g, (unsigned)(5 + g_epi_warps_one) * 32u, hs, stream>>>(p);
+        k_tc_conv<TC_IN_HALO><<<g, (unsigned)(5 + resolve_epi_warps(p.epi_warps)) * 32u, hs, stream>>>(p);
         return cudaGetLastError();
     }
     // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
     const int per_sm = (p.in_mode == TC_IN_PLANES && two_per_sm(p.nt, p.stages)) ? 2 : 1;
-    const int epi_warps = per_sm == 2 ? 4 : g_epi_warps_one;
+    const int epi_warps = per_sm == 2 ? 4 : resolve_epi_warps(p.epi_warps);
     const size_t smem = tc_conv_smem_bytes(p.nt, p.stages, epi_warps);
     if (smem > SMEM_ONE_PER_SM) return cudaErrorInvalidValue;
     const int slots = num_sms * per_sm;

@@ -54,6 +54,7 @@ struct TcConvParams {
     int nt;                  // UMMA N of this layer (multiple of 16, <= 256)
     int stages;              // smem ring depth
     int tmem_cols;           // power of two >= max(32, 2 * nt): two accumulators
+    int epi_warps;           // one CTA per SM: 8 or 16 epilogue warps (0 = build default)
 };
 
 cudaError_t tc_conv_init_device();
@@ -62,12 +63,12 @@ unsigned long long* tc_conv_prof_slot(int slot);
 cudaError_t tc_conv_prof_read(unsigned long long* out, int slots);
 cudaError_t launch_tc_conv(const TcConvParams& p, int num_sms, cudaStream_t stream);
 size_t tc_conv_smem_bytes(int nt, int stages, int epi_warps);
-int tc_conv_pick_stages(int nt, int k_chunks);
+int tc_conv_pick_stages(int nt, int k_chunks, int epi_warps = 0);
 // TC_IN_HALO (3x3 stride-1 pad-1 conv, wout % 128 == 0, cin % 16 == 0): weights resident in smem,
 // each input pixel staged ONCE per tile (3 rows x 130 pixels) and the nine taps read as row-shifted
 // views of that patch.  Returns the number of patch slots (2 or 3) that fit, 0 if the mode does not apply.
-int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks);
-size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots);
+int tc_conv_halo_slots(int k, int stride, int pad, int cin, int wout, int win, int nt, int k_chunks, int epi_warps = 0);
+size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots, int epi_warps = 0);
 // Encodes the 5-D (channel, x, y, segment, plane) fp16 tensor map; returns false if the driver refuses.
 bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
                     const uint32_t box[5], const uint32_t elem_strides[5], int kb);
