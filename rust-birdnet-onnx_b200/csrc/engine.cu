@@ -172,6 +172,7 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
         return set_error(BN_ERR_RUNTIME_INIT, std::string("device '") + prop.name + "' is not sm_100-class; this engine is built for sm_100a only");
     BN_CUDA(init_kernels_for_device());
     BN_CUDA(tc_conv_init_device());
+    BN_CUDA(dw_se_init_device());
     const char* env_tc = getenv("BN_DISABLE_TC");
     const bool tc_enabled = !(env_tc && env_tc[0] == '1');
     e->tc_mode = tc_enabled;
@@ -459,9 +460,16 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
     const Plan& p = e->plan;
     cudaStream_t s = c->stream;
     int prescaled_conv = -1;                   // conv whose gated input was already rescaled in place
+    int fused_se_fc = -1;                      // first FC of a squeeze-excite tail that ran inside the depthwise kernel
+    static const bool no_dw_se = [] { const char* ev = getenv("BN_DISABLE_DW_SE"); return ev && ev[0] == '1'; }();
     for (size_t i = 0; i < p.ops.size(); ++i) {
         const PlanOp& op = p.ops[i];
         const DevOp& d = e->dev_ops[i];
+        if (op.kind == OP_LINEAR && (int)i == fused_se_fc) {
+            prescaled_conv = match_se_tail(p, i);
+            ++i;                                 // both FCs ran inside launch_dw_se
+            continue;
+        }
         if (op.kind == OP_LINEAR) {
             const int cv = match_se_tail(p, i);
             if (cv >= 0 && (p.tensors[p.ops[cv].in].C % 8) == 0) {
@@ -503,6 +511,26 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
         if (op.kind == OP_DWCONV) {
             float* pooled = nullptr;
             if (i + 1 < p.ops.size() && p.ops[i + 1].kind == OP_GAP && p.ops[i + 1].in == op.out) pooled = c->d_tensor[p.ops[i + 1].out];
+            // dw -> pool -> FC silu -> FC sigmoid -> gated conv: one kernel (dw_se.cu)
+            if (pooled && !no_dw_se && i + 3 < p.ops.size()) {
+                const int cv = match_se_tail(p, i + 2);
+                if (cv >= 0 && p.ops[cv].in == op.out && p.ops[i + 2].in == p.ops[i + 1].out) {
+                    const PlanOp &f1 = p.ops[i + 2], &f2 = p.ops[i + 3];
+                    DwSeParams sp{};
+                    sp.in = planes_of(c, op.in); sp.weight = d.weight; sp.bias = d.bias; sp.out = planes_of(c, op.out);
+                    sp.w1 = e->dev_ops[i + 2].weight; sp.b1 = e->dev_ops[i + 2].bias; sp.ldw1 = f1.ldw;
+                    sp.w2 = e->dev_ops[i + 3].weight; sp.b2 = e->dev_ops[i + 3].bias; sp.ldw2 = f2.ldw;
+                    sp.pooled_out = pooled; sp.gate_out = c->d_tensor[f2.out];
+                    sp.batch = B; sp.hin = op.hin; sp.win = op.win; sp.c = op.cout; sp.hout = op.hout; sp.wout = op.wout;
+                    sp.k = op.k; sp.stride = op.stride; sp.pad = op.pad; sp.act = op.act; sp.r = f1.cout;
+                    if (f2.cout == op.cout && f1.cin == op.cout && dw_se_supported(sp)) {
+                        BN_CUDA(launch_dw_se(sp, s));
+                        ++launches;
+                        fused_se_fc = (int)i + 2;
+                        continue;
+                    }
+                }
+            }
             DwPlanesParams dp{planes_of(c, op.in), d.weight, d.bias, planes_of(c, op.out), pooled,
                               B, op.hin, op.win, op.cout, op.hout, op.wout, op.k, op.stride, op.pad, op.act};
             BN_CUDA(launch_dwconv_planes(dp, s));

@@ -112,6 +112,25 @@ cudaError_t launch_se_gate(const float* pooled, const float* w1, const float* b1
                            float* gate, int batch, int c, int r, int ldw1, int ldw2, cudaStream_t stream);
 cudaError_t launch_se_rescale(PlanesPtr d, const float* gate, int batch, int npix, int c, cudaStream_t stream);
 
+// depthwise conv + SiLU + squeeze-excite in one kernel (dw_se.cu): one CTA per segment, un-gated output
+// written, pooled, gated and rescaled in place while it is still L2-resident
+struct DwSeParams {
+    PlanesPtr in;            // [B][hin][win][c] expanded tensor
+    const float* weight;     // [k*k][c]
+    const float* bias;       // [c]
+    PlanesPtr out;           // [B][hout][wout][c] = silu(dw) * gate
+    const float* w1;         // [c][ldw1] (r outputs)
+    const float* b1;         // [r]
+    const float* w2;         // [r][ldw2] (c outputs)
+    const float* b2;         // [c]
+    float* pooled_out;       // [B][c] or nullptr
+    float* gate_out;         // [B][c] or nullptr
+    int batch, hin, win, c, hout, wout, k, stride, pad, act, r, ldw1, ldw2;
+};
+cudaError_t dw_se_init_device();
+bool dw_se_supported(const DwSeParams& p);
+cudaError_t launch_dw_se(const DwSeParams& p, cudaStream_t stream);
+
 // ---- log-mel front-end (row A9: BirdNET v3.0 / Perch v2), frontend_logmel.cu -------------------
 struct LogmelParams {
     const float* audio;       // [B][sample_count] raw samples

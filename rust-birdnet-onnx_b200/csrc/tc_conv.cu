@@ -371,6 +371,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 const int ky = tap / 3, kx = tap - ky * 3;
                 const int k = tap * p.cin + ks * 16;
                 halo_a16[i] = ((uint32_t)(2 * ks) * lbo + (uint32_t)(ky * HALO_W + kx) * 16u) >> 4;   // row m <-> patch pixel m + ky*130 + kx
+                if (p.debug_flags & 1) halo_a16[i] &= ~7u;
                 halo_db[i] = umma_desc_sw128(smem_u32(tiles) + (uint32_t)(k >> 6) * w_bytes) + (uint64_t)(kDescKStep * ((k & 63) >> 4));
             }
             __syncwarp();
@@ -670,6 +671,7 @@ cudaError_t tc_conv_init_device() {
 cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t stream) {
     if (pin.M <= 0) return cudaSuccess;
     TcConvParams p = pin;
+    { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("BN_TC_DEBUG"); dbg = ev ? atoi(ev) : 0; } p.debug_flags = dbg; }
     if (p.in_mode != TC_IN_TMA || p.tiles_per_seg <= 0) {      // cp.async modes: one flat "segment"
         if (p.in_mode != TC_IN_TMA) { p.tiles_per_seg = p.m_tiles; p.pix_per_seg = p.M; }
     }

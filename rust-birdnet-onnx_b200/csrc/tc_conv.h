@@ -55,6 +55,7 @@ struct TcConvParams {
     int stages;              // smem ring depth
     int tmem_cols;           // power of two >= max(32, 2 * nt): two accumulators
     int epi_warps;           // one CTA per SM: 8 or 16 epilogue warps (0 = build default)
+    int debug_flags;         // development experiments (BN_TC_DEBUG), 0 in production
 };
 
 cudaError_t tc_conv_init_device();
