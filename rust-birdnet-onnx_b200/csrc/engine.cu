@@ -455,13 +455,60 @@ static int match_se_tail(const Plan& p, size_t i) {
     return -1;
 }
 
+static bool no_dw_se_flag() {
+    static const bool v = [] { const char* ev = getenv("BN_DISABLE_DW_SE"); return ev && ev[0] == '1'; }();
+    return v;
+}
+
 static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
     bn_engine* e = c->eng;
     const Plan& p = e->plan;
     cudaStream_t s = c->stream;
     int prescaled_conv = -1;                   // conv whose gated input was already rescaled in place
+    // FP32 hand-off: a tensor-core conv whose output is read by exactly one op, a depthwise conv that runs in the
+    // fused dw + squeeze-excite kernel, writes plain FP32 (dw_se.cu lands it in shared memory with cp.async)
+    static const bool no_f32_handoff = [] { const char* ev = getenv("BN_DISABLE_F32_HANDOFF"); return ev && ev[0] == '1'; }();
+    auto sole_dw_consumer = [&](int t) -> int {
+        int found = -1, uses = 0;
+        for (size_t q = 0; q < p.ops.size(); ++q) {
+            const PlanOp& o = p.ops[q];
+            if (o.in == t) { ++uses; if (o.kind == OP_DWCONV) found = (int)q; }
+            if (o.residual == t || o.in_scale == t) ++uses;
+        }
+        for (auto& o : p.outputs) if (p.root(o.tensor) == p.root(t)) ++uses;
+        return uses == 1 ? found : -1;
+    };
+    auto producer_of = [&](int t) -> int {
+        for (size_t q = 0; q < p.ops.size(); ++q) if (p.ops[q].out == t) return (int)q;
+        return -1;
+    };
+    // would the depthwise conv at `i` run fused, and with which input form?  fills sp on success
+    auto dw_se_plan = [&](size_t i, DwSeParams& sp) -> int {
+        const PlanOp& op = p.ops[i];
+        if (op.kind != OP_DWCONV || no_dw_se_flag() || i + 3 >= p.ops.size()) return -1;
+        if (!(p.ops[i + 1].kind == OP_GAP && p.ops[i + 1].in == op.out)) return -1;
+        const int cv = match_se_tail(p, i + 2);
+        if (cv < 0 || p.ops[cv].in != op.out || p.ops[i + 2].in != p.ops[i + 1].out) return -1;
+        const PlanOp &f1 = p.ops[i + 2], &f2 = p.ops[i + 3];
+        if (f2.cout != op.cout || f1.cin != op.cout) return -1;
+        sp = DwSeParams{};
+        sp.in = planes_of(c, op.in); sp.weight = e->dev_ops[i].weight; sp.bias = e->dev_ops[i].bias; sp.out = planes_of(c, op.out);
+        sp.w1 = e->dev_ops[i + 2].weight; sp.b1 = e->dev_ops[i + 2].bias; sp.ldw1 = f1.ldw;
+        sp.w2 = e->dev_ops[i + 3].weight; sp.b2 = e->dev_ops[i + 3].bias; sp.ldw2 = f2.ldw;
+        sp.pooled_out = c->d_tensor[p.ops[i + 1].out]; sp.gate_out = c->d_tensor[f2.out];
+        sp.batch = B; sp.hin = op.hin; sp.win = op.win; sp.c = op.cout; sp.hout = op.hout; sp.wout = op.wout;
+        sp.k = op.k; sp.stride = op.stride; sp.pad = op.pad; sp.act = op.act; sp.r = f1.cout;
+        // FP32 input when the producer is a tensor-core conv with a vectorisable epilogue and this is its only reader
+        const int prod = producer_of(op.in);
+        if (!no_f32_handoff && prod >= 0 && e->dev_ops[prod].use_tc && p.ops[prod].kind == OP_CONV && (p.ops[prod].cout & 15) == 0 &&
+            is_spatial(p, op.in) && sole_dw_consumer(op.in) == (int)i) {
+            sp.in_f32 = c->d_tensor[op.in];
+            if (dw_se_supported(sp)) return cv;
+            sp.in_f32 = nullptr;
+        }
+        return dw_se_supported(sp) ? cv : -1;
+    };
     int fused_se_fc = -1;                      // first FC of a squeeze-excite tail that ran inside the depthwise kernel
-    static const bool no_dw_se = [] { const char* ev = getenv("BN_DISABLE_DW_SE"); return ev && ev[0] == '1'; }();
     for (size_t i = 0; i < p.ops.size(); ++i) {
         const PlanOp& op = p.ops[i];
         const DevOp& d = e->dev_ops[i];
@@ -512,23 +559,13 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             float* pooled = nullptr;
             if (i + 1 < p.ops.size() && p.ops[i + 1].kind == OP_GAP && p.ops[i + 1].in == op.out) pooled = c->d_tensor[p.ops[i + 1].out];
             // dw -> pool -> FC silu -> FC sigmoid -> gated conv: one kernel (dw_se.cu)
-            if (pooled && !no_dw_se && i + 3 < p.ops.size()) {
-                const int cv = match_se_tail(p, i + 2);
-                if (cv >= 0 && p.ops[cv].in == op.out && p.ops[i + 2].in == p.ops[i + 1].out) {
-                    const PlanOp &f1 = p.ops[i + 2], &f2 = p.ops[i + 3];
-                    DwSeParams sp{};
-                    sp.in = planes_of(c, op.in); sp.weight = d.weight; sp.bias = d.bias; sp.out = planes_of(c, op.out);
-                    sp.w1 = e->dev_ops[i + 2].weight; sp.b1 = e->dev_ops[i + 2].bias; sp.ldw1 = f1.ldw;
-                    sp.w2 = e->dev_ops[i + 3].weight; sp.b2 = e->dev_ops[i + 3].bias; sp.ldw2 = f2.ldw;
-                    sp.pooled_out = pooled; sp.gate_out = c->d_tensor[f2.out];
-                    sp.batch = B; sp.hin = op.hin; sp.win = op.win; sp.c = op.cout; sp.hout = op.hout; sp.wout = op.wout;
-                    sp.k = op.k; sp.stride = op.stride; sp.pad = op.pad; sp.act = op.act; sp.r = f1.cout;
-                    if (f2.cout == op.cout && f1.cin == op.cout && dw_se_supported(sp)) {
-                        BN_CUDA(launch_dw_se(sp, s));
-                        ++launches;
-                        fused_se_fc = (int)i + 2;
-                        continue;
-                    }
+            {
+                DwSeParams sp;
+                if (dw_se_plan(i, sp) >= 0) {
+                    BN_CUDA(launch_dw_se(sp, s));
+                    ++launches;
+                    fused_se_fc = (int)i + 2;
+                    continue;
                 }
             }
             DwPlanesParams dp{planes_of(c, op.in), d.weight, d.bias, planes_of(c, op.out), pooled,
@@ -572,7 +609,16 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
                 tp.res_hi = rp.hi; tp.res_plane = rp.plane;
             }
             tp.bias = d.bias;
-            if (is_spatial(p, op.out)) {
+            bool f32_rows = false;
+            if (is_spatial(p, op.out) && op.kind == OP_CONV && (op.cout & 15) == 0) {
+                const int dwi = sole_dw_consumer(op.out);
+                DwSeParams sp;
+                f32_rows = dwi >= 0 && dw_se_plan((size_t)dwi, sp) >= 0 && sp.in_f32 != nullptr;
+            }
+            if (f32_rows) {
+                tp.out_f32 = c->d_tensor[op.out];
+                tp.out_f32_rows = 1;
+            } else if (is_spatial(p, op.out)) {
                 PlanesPtr o = planes_of(c, op.out);
                 tp.out_hi = o.hi; tp.out_plane = o.plane;
             } else {

@@ -889,23 +889,39 @@ cudaError_t launch_se_rescale(PlanesPtr d, const float* gate, int batch, int npi
 // Stem: direct k x k conv for tiny Cin (the 2-channel spectrogram), planes in / planes out.
 // One thread per output pixel computes all Cout (<= 32) channels; weights live in smem.
 // ======================================================================================
-// CTA = one strip of STRIP output pixels of one output row; the k input rows it needs are staged
-// in smem as FP32; thread = (pixel slot, channel quad) with its k*k*cin x 4 weights in registers.
-template <int K, int CIN, int STRIDE, int STRIP>
-__global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
+// CTA = one strip of STRIP output pixels of one output row; the 3 input rows it needs are staged in smem
+// as FP32 with every value DUPLICATED (x, x), which is the multiplicand layout of the packed FFMA2
+// (fma.rn.f32x2): thread = (pixel slot, channel quad), its 9*cin x 4 weights live in registers as two
+// f32x2 pairs per tap, so a tap costs one LDS and two (cin = 1) or four (cin = 2) FFMA2.
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float silu_fast_k(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+template <int CIN, int STRIP>
+__global__ void __launch_bounds__(256, 2) k_stem_planes(ConvPlanesParams p) {
+    constexpr int K = 3, STRIDE = 2;
     constexpr int WIN = (STRIP - 1) * STRIDE + K;               // input columns per strip
-    __shared__ float s_x[K][WIN * CIN];
+    __shared__ __align__(16) float s_x[K][WIN * CIN * 2];
     const int quads = p.cout >> 2;                               // 8 for cout = 32
     const int slots = 256 / quads;                               // pixel slots per pass
     const int strips = (p.wout + STRIP - 1) / STRIP;
     const int q = threadIdx.x % quads, slot = threadIdx.x / quads;
-    float w[K * K * CIN][4];
+    unsigned long long w[K * K * CIN][2];
 #pragma unroll
     for (int t = 0; t < K * K * CIN; ++t) {
         const float4 wv = *reinterpret_cast<const float4*>(p.weight + (size_t)t * p.ldw + q * 4);
-        w[t][0] = wv.x; w[t][1] = wv.y; w[t][2] = wv.z; w[t][3] = wv.w;
+        w[t][0] = pack_f2(wv.x, wv.y);
+        w[t][1] = pack_f2(wv.z, wv.w);
     }
     const float4 bv = *reinterpret_cast<const float4*>(p.bias + q * 4);
+    const unsigned long long b01 = pack_f2(bv.x, bv.y), b23 = pack_f2(bv.z, bv.w);
+    const bool silu = p.act == KACT_SILU;
     const int total = p.batch * p.hout * strips;
     for (int work = blockIdx.x; work < total; work += gridDim.x) {     // persistent: weights stay in registers
     const int strip = work % strips;
@@ -951,29 +967,43 @@ __global__ void __launch_bounds__(256) k_stem_planes(ConvPlanesParams p) {
             const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vh[j]));
             const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&vl[j]));
             if (CIN == 2) {
-                s_x[ky][x * 2] = a.x + d.x;
-                s_x[ky][x * 2 + 1] = a.y + d.y;
+                const float x0 = a.x + d.x, x1 = a.y + d.y;
+                *reinterpret_cast<float4*>(&s_x[ky][x * 4]) = make_float4(x0, x0, x1, x1);
             } else {
-                s_x[ky][x] = a.x + d.x;
+                const float x0 = a.x + d.x;
+                *reinterpret_cast<float2*>(&s_x[ky][x * 2]) = make_float2(x0, x0);
             }
         }
     }
     __syncthreads();
     for (int px = slot; px < STRIP && ox0 + px < p.wout; px += slots) {
-        float acc[4] = {bv.x, bv.y, bv.z, bv.w};
+        unsigned long long a01 = b01, a23 = b23;
 #pragma unroll
         for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < K; ++kx)
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    const float x = s_x[ky][(px * STRIDE + kx) * CIN + ci];
-                    const int t = (ky * K + kx) * CIN + ci;
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) acc[n] = fmaf(x, w[t][n], acc[n]);
+            for (int kx = 0; kx < K; ++kx) {
+                const int t = (ky * K + kx) * CIN;
+                if (CIN == 2) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&s_x[ky][(px * STRIDE + kx) * 4]);
+                    a01 = ffma2(v.x, w[t][0], a01);
+                    a23 = ffma2(v.x, w[t][1], a23);
+                    a01 = ffma2(v.y, w[t + 1][0], a01);
+                    a23 = ffma2(v.y, w[t + 1][1], a23);
+                } else {
+                    const unsigned long long v = *reinterpret_cast<const unsigned long long*>(&s_x[ky][(px * STRIDE + kx) * 2]);
+                    a01 = ffma2(v, w[t][0], a01);
+                    a23 = ffma2(v, w[t][1], a23);
                 }
+            }
+        float acc[4] = {__uint_as_float((uint32_t)a01), __uint_as_float((uint32_t)(a01 >> 32)),
+                        __uint_as_float((uint32_t)a23), __uint_as_float((uint32_t)(a23 >> 32))};
+        if (silu) {
 #pragma unroll
-        for (int n = 0; n < 4; ++n) acc[n] = apply_act(acc[n], p.act);
+            for (int n = 0; n < 4; ++n) acc[n] = silu_fast_k(acc[n]);
+        } else {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) acc[n] = apply_act(acc[n], p.act);
+        }
         const __half2 h0 = __floats2half2_rn(acc[0], acc[1]), h1 = __floats2half2_rn(acc[2], acc[3]);
         const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
         const __half2 l0 = __floats2half2_rn(acc[0] - b0.x, acc[1] - b0.y), l1 = __floats2half2_rn(acc[2] - b1.x, acc[3] - b1.y);
@@ -991,16 +1021,18 @@ cudaError_t launch_stem_planes(const ConvPlanesParams& p, cudaStream_t stream) {
     if (p.batch <= 0) return cudaSuccess;
     if (p.k != 3 || (p.cin != 2 && p.cin != 1) || p.stride != 2 || (p.cout & 3) || p.cout > 64 || (256 % (p.cout >> 2)) || p.in_scale || p.residual.hi)
         return cudaErrorInvalidValue;
-    const int strip = p.wout > 64 ? 128 : 64;
+    const int strip = p.wout > 128 ? 256 : (p.wout > 64 ? 128 : 64);
     const int strips = (p.wout + strip - 1) / strip;
     const long long total = (long long)p.batch * p.hout * strips;
-    const int grid = (int)(total < 148 * 6 ? total : 148 * 6);
+    const int grid = (int)(total < 148 * 2 ? total : 148 * 2);
     if (p.cin == 2) {
-        if (strip == 128) k_stem_planes<3, 2, 2, 128><<<grid, 256, 0, stream>>>(p);
-        else k_stem_planes<3, 2, 2, 64><<<grid, 256, 0, stream>>>(p);
+        if (strip == 256) k_stem_planes<2, 256><<<grid, 256, 0, stream>>>(p);
+        else if (strip == 128) k_stem_planes<2, 128><<<grid, 256, 0, stream>>>(p);
+        else k_stem_planes<2, 64><<<grid, 256, 0, stream>>>(p);
     } else {
-        if (strip == 128) k_stem_planes<3, 1, 2, 128><<<grid, 256, 0, stream>>>(p);
-        else k_stem_planes<3, 1, 2, 64><<<grid, 256, 0, stream>>>(p);
+        if (strip == 256) k_stem_planes<1, 256><<<grid, 256, 0, stream>>>(p);
+        else if (strip == 128) k_stem_planes<1, 128><<<grid, 256, 0, stream>>>(p);
+        else k_stem_planes<1, 64><<<grid, 256, 0, stream>>>(p);
     }
     return cudaGetLastError();
 }

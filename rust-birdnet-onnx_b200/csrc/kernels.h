@@ -115,7 +115,8 @@ cudaError_t launch_se_rescale(PlanesPtr d, const float* gate, int batch, int npi
 // depthwise conv + SiLU + squeeze-excite in one kernel (dw_se.cu): one CTA per segment, un-gated output
 // written, pooled, gated and rescaled in place while it is still L2-resident
 struct DwSeParams {
-    PlanesPtr in;            // [B][hin][win][c] expanded tensor
+    PlanesPtr in;            // [B][hin][win][c] expanded tensor as hi/lo planes (used when in_f32 == nullptr)
+    const float* in_f32;     // the same tensor as plain FP32 (its producer wrote it for this kernel alone), or nullptr
     const float* weight;     // [k*k][c]
     const float* bias;       // [c]
     PlanesPtr out;           // [B][hout][wout][c] = silu(dw) * gate
@@ -126,6 +127,7 @@ struct DwSeParams {
     float* pooled_out;       // [B][c] or nullptr
     float* gate_out;         // [B][c] or nullptr
     int batch, hin, win, c, hout, wout, k, stride, pad, act, r, ldw1, ldw2;
+    int debug;               // development experiments (BN_DW_DEBUG), 0 in production
 };
 cudaError_t dw_se_init_device();
 bool dw_se_supported(const DwSeParams& p);

@@ -467,7 +467,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         float* stg = reinterpret_cast<float*>(tiles + ring_bytes + (size_t)ew * EPI_STAGE_BYTES);
         uint32_t it = 0;
         const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
-        const bool staged = vec && p.out_f32 == nullptr && p.spec_nframes == 0;
+        const bool staged = vec && (p.out_f32 == nullptr || p.out_f32_rows) && p.spec_nframes == 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int mt = p.n_tiles == 1 ? t : t / p.n_tiles;
             const int n_tile = p.n_tiles == 1 ? 0 : t - mt * p.n_tiles;
@@ -539,10 +539,15 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) w8[e] += fh[e] + fl[e];
                             }
-                            uint4 hi, lo;
-                            split8(w8, hi, lo);
-                            *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
-                            *reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o) = lo;
+                            if (p.out_f32) {
+                                *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                                *reinterpret_cast<float4*>(p.out_f32 + o + 4) = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                            } else {
+                                uint4 hi, lo;
+                                split8(w8, hi, lo);
+                                *reinterpret_cast<uint4*>(p.out_hi + o) = hi;
+                                *reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o) = lo;
+                            }
                         }
                     }
                     __syncwarp();                                  // staging tile free for the next group

@@ -41,6 +41,7 @@ struct TcConvParams {
     __half* out_hi;
     size_t out_plane;
     float* out_f32;
+    int out_f32_rows;        // 1: out_f32 is a spatial [M][cout] FP32 tensor written by the staged (coalesced) epilogue
     int spec_nframes, spec_nch, spec_ch;
     float spec_exponent;
     const void* wpack;       // [n_tiles][k_chunks][hi|lo][nt x 64] fp16, SW128 K-major smem images
