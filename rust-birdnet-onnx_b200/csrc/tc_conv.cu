@@ -96,10 +96,12 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     const bool prof = p.prof != nullptr && blockIdx.x == 0;
     unsigned long long pw0 = 0, pw1 = 0;
     const long long prof_t0 = prof ? clock64() : 0;
-    const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * (uint32_t)NT * 128u;
     const uint32_t w_bytes = 2u * (uint32_t)NT * 128u;
+    const bool w_res = MODE == TC_IN_TMA && p.w_resident != 0;        // weights of this CTA's n tile resident, ring = A tiles only
+    const uint32_t stage_bytes = 2u * A_TILE_BYTES + (w_res ? 0u : w_bytes);
     const int total_tiles = p.m_tiles * p.n_tiles;
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = tiles0 + (w_res ? (size_t)p.k_chunks * w_bytes : 0);     // ring base (resident weights, if any, sit in front of it)
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -141,7 +143,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     uint8_t* halo_slots = tiles + (size_t)p.k_chunks * w_bytes;
     // the epilogue staging tiles start after the ring
     const size_t ring_bytes = MODE == TC_IN_HALO ? (size_t)p.k_chunks * w_bytes + (size_t)STAGES * halo_slot_bytes
-                                                 : (size_t)STAGES * stage_bytes;
+                                                 : (size_t)STAGES * stage_bytes;      // measured from `tiles`
     if (MODE == TC_IN_HALO && warp < 4) {
         // ================================ halo-patch producers ================================
         const int n_tile = blockIdx.x % p.n_tiles;               // fixed per CTA (grid % n_tiles == 0)
@@ -201,6 +203,15 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         // ================================ TMA producer (one thread) ================================
         if (tid == 0) {
             tma_prefetch_desc(&p.tmap);
+            if (w_res) {
+                const int n_res = blockIdx.x % p.n_tiles;                 // fixed per CTA (grid % n_tiles == 0)
+                asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
+                             ::"r"(smem_u32(&bar_w)), "r"((uint32_t)p.k_chunks * w_bytes) : "memory");
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)n_res * p.k_chunks + kc) * w_bytes;
+                    bulk_copy_g2s(tiles0 + (size_t)kc * w_bytes, src, w_bytes, &bar_w);
+                }
+            }
             const uint32_t sub_bytes = (uint32_t)TM * (uint32_t)p.kb * 2u;       // one [128][kb] fp16 box
             const int subs_per_chunk = KC / p.kb;
             uint32_t s = 0, ph = 0;
@@ -225,7 +236,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                     int nsub = (p.K - kc * KC + p.kb - 1) / p.kb;
                     if (nsub > subs_per_chunk) nsub = subs_per_chunk;
                     asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
-                                 ::"r"(smem_u32(&bar_full[s])), "r"(w_bytes + 2u * (uint32_t)nsub * sub_bytes) : "memory");
+                                 ::"r"(smem_u32(&bar_full[s])), "r"((w_res ? 0u : w_bytes) + 2u * (uint32_t)nsub * sub_bytes) : "memory");
                     for (int sb = 0; sb < nsub; ++sb) {
                         const int k0 = kc * KC + sb * p.kb;
                         const int tap = k0 / p.tab_cin, ci = k0 - tap * p.tab_cin;
@@ -233,8 +244,10 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         tma_load_5d(st + (size_t)sb * sub_bytes, &p.tmap, ci, x0 + kx, y0 + ky, seg, 0, &bar_full[s]);
                         tma_load_5d(st + A_TILE_BYTES + (size_t)sb * sub_bytes, &p.tmap, ci, x0 + kx, y0 + ky, seg, 1, &bar_full[s]);
                     }
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)n_tile * p.k_chunks + kc) * w_bytes;
-                    bulk_copy_g2s(st + 2 * A_TILE_BYTES, src, w_bytes, &bar_full[s]);
+                    if (!w_res) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)n_tile * p.k_chunks + kc) * w_bytes;
+                        bulk_copy_g2s(st + 2 * A_TILE_BYTES, src, w_bytes, &bar_full[s]);
+                    }
                     if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }
                 }
             }
@@ -404,6 +417,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         } else if (MODE != TC_IN_HALO && lane == 0) {
             const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
+            if (w_res) mbar_wait(&bar_w, 0);
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const uint32_t a = it & 1u;
@@ -415,7 +429,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                     fence_proxy_async_smem();          // cp.async / st.shared (generic proxy) -> tcgen05 reads (async proxy)
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t db_hi = umma_desc_sw128(a_hi + 2 * A_TILE_BYTES);   // [W_hi | W_lo]: 2NT rows
+                    const uint64_t db_hi = umma_desc_sw128(w_res ? smem_u32(tiles0) + (uint32_t)kc * w_bytes : a_hi + 2 * A_TILE_BYTES);   // [W_hi | W_lo]: 2NT rows
                     int ksteps = (p.K - kc * KC + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
                     if (MODE != TC_IN_TMA) {
@@ -440,7 +454,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                             const uint64_t da_lo = umma_desc_kmajor(a_hi + A_TILE_BYTES + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
                             const uint64_t adv = (uint64_t)(kDescKStep * j);
                             umma_f16(acc, da_hi, db_hi + adv, idesc2, (kc | j) != 0 ? 1u : 0u);
-                            umma_f16(acc + (uint32_t)NT, da_lo, db_hi + adv, idesc1, 1u);
+                            if (!(p.debug_flags & 4)) umma_f16(acc + (uint32_t)NT, da_lo, db_hi + adv, idesc1, 1u);
                         }
                     }
                     umma_commit(&bar_empty[s]);        // frees the smem stage when these MMAs retire
@@ -467,7 +481,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         float* stg = reinterpret_cast<float*>(tiles + ring_bytes + (size_t)ew * EPI_STAGE_BYTES);
         uint32_t it = 0;
         const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
-        const bool staged = vec && (p.out_f32 == nullptr || p.out_f32_rows) && p.spec_nframes == 0;
+        const bool staged = vec && (p.out_f32 == nullptr || p.out_f32_rows) && p.spec_nframes == 0;   // measured: per-lane direct FP32 row stores are 10-35% slower than the staged, coalesced ones
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int mt = p.n_tiles == 1 ? t : t / p.n_tiles;
             const int n_tile = p.n_tiles == 1 ? 0 : t - mt * p.n_tiles;
@@ -481,7 +495,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const int row = sb * p.pix_per_seg + lp;
             const bool row_ok = lp < p.pix_per_seg && row < p.M;
             const uint32_t t_lane = tmem_base + a * 2u * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
-            if (staged) {
+            if (p.debug_flags & 2) {
+            } else if (staged) {
                 for (int c0 = cset * 32; c0 < NT; c0 += 32 * nsets) {
                     const int gw = NT - c0 < 32 ? 16 : 32;         // NT is a multiple of 16
                     for (int h = 0; h < gw; h += 16) {
@@ -707,6 +722,24 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
     const int slots = num_sms * per_sm;
     dim3 grid((unsigned)(total < slots ? total : slots));
     const unsigned nthr = (unsigned)(5 + epi_warps) * 32u;
+    if (p.in_mode == TC_IN_TMA) {
+        // weights resident when this CTA's whole [K x NT] tile plus a >= 3 deep A ring fit: halves the L2 -> SM traffic of
+        // shallow-K layers (expand 1x1 convs).  Measured: -8% with the epilogue switched off, ~1% with it on - these
+        // layers are bound by the epilogue warps (tools/tc_role_profile.py), not by operand traffic or the tensor pipe.
+        static const bool no_wres = [] { const char* ev = getenv("BN_DISABLE_WRES"); return ev && ev[0] == '1'; }();
+        const size_t wres = (size_t)p.k_chunks * 2 * p.nt * 128;
+        const size_t fixed = 1024 + (size_t)epi_warps * EPI_STAGE_BYTES + wres;
+        int g = (int)grid.x - (int)grid.x % p.n_tiles;
+        if (!no_wres && fixed + 3 * (size_t)(2 * A_TILE_BYTES) <= SMEM_ONE_PER_SM && g >= p.n_tiles && p.m_tiles >= 2 * (g / p.n_tiles)) {
+            int st = (int)((SMEM_ONE_PER_SM - fixed) / (2 * A_TILE_BYTES));
+            if (st > MAX_STAGES) st = MAX_STAGES;
+            p.w_resident = 1;
+            p.stages = st;
+            const size_t smem_res = fixed + (size_t)st * 2 * A_TILE_BYTES;
+            k_tc_conv<TC_IN_TMA><<<g, nthr, smem_res, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
     switch (p.in_mode) {
         case TC_IN_PLANES:
             if (per_sm == 2) k_tc_conv<TC_IN_PLANES, true><<<grid, nthr, smem, stream>>>(p);

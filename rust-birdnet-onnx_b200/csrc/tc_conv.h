@@ -57,6 +57,7 @@ struct TcConvParams {
     int tmem_cols;           // power of two >= max(32, 2 * nt): two accumulators
     int epi_warps;           // one CTA per SM: 8 or 16 epilogue warps (0 = build default)
     int debug_flags;         // development experiments (BN_TC_DEBUG), 0 in production
+    int w_resident;          // TC_IN_TMA: this CTA's weight tile (all K chunks) stays in smem, the ring carries A only; set by launch_tc_conv
 };
 
 cudaError_t tc_conv_init_device();
