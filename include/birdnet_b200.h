@@ -152,6 +152,14 @@ uint64_t bn_ctx_input_buffer_bytes(const bn_ctx* ctx); /* batch_context.rs:155-1
  * GPU (bench: inputs already in HBM).  fetch_outputs != 0 copies results to the pinned host slab. */
 int bn_ctx_run_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs,
                       const bn_run_opts* opts, bn_outputs* out);
+/* CLI ingest with the conversion and chunking on the device (replaces, for callers
+ * that hold the recording as 16-bit PCM, read_wav's i16 -> f32 / 32768 (src/bin/birdnet-analyze.rs:21, 684-687)
+ * and chunk_audio (src/bin/birdnet-analyze.rs:707-743)): segment b of this call covers samples
+ * [first_pos + b*step, first_pos + b*step + sample_count) of `pcm` (n_samples long), zero-padded past the end.
+ * step = sample_count - overlap_samples, 1 <= step <= sample_count; batch <= max_batch_size.  The recording
+ * crosses PCIe once, 2 bytes per sample, overlap not duplicated.  Outputs as bn_ctx_run. */
+int bn_ctx_run_pcm16(bn_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t first_pos, uint64_t step,
+                     uint64_t batch, const bn_run_opts* opts, bn_outputs* out);
 /* Asynchronous halves of bn_ctx_run_device: enqueue returns once the work is on the stream;
  * several enqueues may be queued back to back (each overwrites the previous outputs); wait blocks
  * (polling opts) until everything enqueued so far has finished and exposes the last outputs. */

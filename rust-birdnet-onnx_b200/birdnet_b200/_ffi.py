@@ -87,6 +87,7 @@ SIGNATURES = {
     "bn_ctx_max_batch_size": (C.c_uint64, [_vp]),
     "bn_ctx_input_buffer_bytes": (C.c_uint64, [_vp]),
     "bn_ctx_run_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int32, _P(RunOpts), _P(Outputs)]),
+    "bn_ctx_run_pcm16": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P(RunOpts), _P(Outputs)]),
     "bn_ctx_enqueue_device": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int32]),
     "bn_ctx_wait": (C.c_int, [_vp, _P(RunOpts), _P(Outputs)]),
     "bn_ctx_read_tensor": (C.c_int, [_vp, C.c_char_p, _P(C.c_float), C.c_uint64, _P(C.c_uint64)]),

@@ -307,6 +307,44 @@ class Classifier:
         raise_for_status(st, timeout)
         return self._results(out)
 
+    def predict_pcm16_stream(self, context: BatchInferenceContext, pcm, overlap_secs: float = 0.0,
+                             options: Optional[InferenceOptions] = None):
+        """The analysis loop of the reference CLI (src/bin/birdnet-analyze.rs:520-640) for a recording held as
+        16-bit mono PCM at the model's sample rate: read_wav's i16 -> f32 / 32768 conversion (653-704) and
+        chunk_audio (707-743) run on the device, so the recording crosses PCIe once at 2 bytes per sample.
+        Returns [(start_time_secs, PredictionResult)] in recording order, like the CLI's `(f32, Vec<f32>)`
+        segment list joined with its results."""
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.dtype != np.int16 or pcm.ndim != 1:
+            from .errors import AudioFormat
+            raise AudioFormat("PCM must be a 1-D int16 array (mono, 16-bit)")
+        if pcm.size == 0:                                        # birdnet-analyze.rs:694-698
+            from .errors import AudioFormat
+            raise AudioFormat("WAV file has no samples")
+        cfg = self._config
+        S, sr = cfg.sample_count, cfg.sample_rate
+        # f32 arithmetic and truncation exactly as `(overlap_secs * sample_rate as f32) as usize` (712-718)
+        overlap = int(np.float32(overlap_secs) * np.float32(sr))
+        step = max(S - max(overlap, 0), 0)                       # saturating_sub
+        if step == 0:
+            return []
+        n = int(pcm.size)
+        n_seg = (n + step - 1) // step                           # while pos < samples.len()
+        B = context.max_batch_size()
+        ro, timeout = _run_opts(options)
+        results = []
+        ptr = pcm.ctypes.data_as(C.c_void_p)
+        for first in range(0, n_seg, B):
+            nb = min(B, n_seg - first)
+            out = _ffi.Outputs()
+            st = _lib.bn_ctx_run_pcm16(context._h, ptr, n, first * step, step, nb,
+                                       C.byref(ro) if ro is not None else None, C.byref(out))
+            raise_for_status(st, timeout)
+            res = self._results(out)
+            for j, r in enumerate(res):
+                results.append((float(np.float32((first + j) * step) / np.float32(sr)), r))
+        return results
+
     def _run_engine(self, segments, options) -> List[PredictionResult]:
         ptrs, lens, keep = _segment_arrays(segments)
         ro, timeout = _run_opts(options)

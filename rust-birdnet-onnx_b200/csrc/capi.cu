@@ -168,6 +168,11 @@ int bn_ctx_run_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t
     return ctx_run_device(ctx, d_audio, batch, fetch_outputs != 0, opts, out);
 }
 
+int bn_ctx_run_pcm16(bn_ctx* ctx, const int16_t* pcm, uint64_t n_samples, uint64_t first_pos, uint64_t step, uint64_t batch,
+                     const bn_run_opts* opts, bn_outputs* out) {
+    return ctx_run_pcm16(ctx, pcm, n_samples, first_pos, step, batch, opts, out);
+}
+
 int bn_ctx_enqueue_device(bn_ctx* ctx, const float* d_audio, uint64_t batch, int32_t fetch_outputs) {
     if (!d_audio && batch) return set_error(BN_ERR_INVALID_ARGUMENT, "null device buffer");
     return ctx_enqueue_device(ctx, d_audio, batch, fetch_outputs != 0, nullptr);

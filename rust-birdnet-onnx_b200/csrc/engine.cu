@@ -329,6 +329,8 @@ bn_ctx::~bn_ctx() {
     cudaSetDevice(eng->device);
     if (stream) cudaStreamSynchronize(stream);
     if (h_in) cudaFreeHost(h_in);
+    if (h_pcm) cudaFreeHost(h_pcm);
+    if (d_pcm) cudaFree(d_pcm);
     if (d_in) cudaFree(d_in);
     if (d_norm) cudaFree(d_norm);
     if (d_minmax) cudaFree(d_minmax);
@@ -967,6 +969,56 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
         size_t n = c->prof_names.size();
         c->prof_ms.assign(n ? n - 1 : 0, 0.f);
         for (size_t i = 0; i + 1 < n; ++i) cudaEventElapsedTime(&c->prof_ms[i], c->prof_events[i], c->prof_events[i + 1]);
+    }
+    return BN_OK;
+}
+
+// CLI ingest (src/bin/birdnet-analyze.rs:653-743) with the conversion and the chunking on the device: the
+// recording crosses PCIe once as 16-bit PCM (2 B/sample, overlap not duplicated) instead of as FP32 segments.
+int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t first_pos, uint64_t step, uint64_t batch,
+                  const bn_run_opts* opts, bn_outputs* out) {
+    if (!c || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (batch == 0) { memset(out, 0, sizeof(*out)); return BN_OK; }
+    if (!pcm) return set_error(BN_ERR_INVALID_ARGUMENT, "null pcm buffer");
+    bn_engine* e = c->eng;
+    const uint64_t S = (uint64_t)e->plan.sample_count;
+    if (batch > c->max_batch)
+        return set_error(BN_ERR_INFERENCE, "batch size " + std::to_string(batch) + " exceeds context max " + std::to_string(c->max_batch));
+    if (step == 0 || step > S) return set_error(BN_ERR_INVALID_ARGUMENT, "step must be in [1, sample_count]");
+    if (first_pos >= n_samples) return set_error(BN_ERR_INVALID_ARGUMENT, "first segment starts past the end of the recording");
+    PostCfg post;
+    uint64_t k_eff = 0;
+    int st = begin_run(c, post, k_eff, opts);
+    if (st != BN_OK) return st;
+    const size_t cap = (size_t)c->max_batch * S;
+    if (!c->h_pcm) {
+        BN_CUDA(cudaHostAlloc(&c->h_pcm, cap * sizeof(int16_t), cudaHostAllocDefault));
+        BN_CUDA(cudaMalloc(&c->d_pcm, cap * sizeof(int16_t)));
+    }
+    const uint64_t hi = std::min<uint64_t>(n_samples, first_pos + (batch - 1) * step + S);
+    const size_t n = (size_t)(hi - first_pos);                      // <= (batch-1)*step + S <= max_batch * S
+    prof_mark(c, "h2d");
+    const size_t piece = (size_t)4 << 20;                           // samples per pipelined copy (8 MiB)
+    for (size_t o = 0; o < n; o += piece) {
+        const size_t m = std::min(piece, n - o);
+        memcpy(c->h_pcm + o, pcm + first_pos + o, m * sizeof(int16_t));
+        BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, c->h_pcm + o, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    BN_CUDA(launch_pcm16_to_segments(c->d_pcm, first_pos, n_samples, first_pos, step, c->d_in, (int)batch, (int)S, c->stream));
+    st = enqueue_forward(c, c->d_in, (int)batch, post, k_eff);
+    if (st != BN_OK) return st;
+    c->last_launches += 1;
+    st = enqueue_fetch(c, (int)batch, k_eff);
+    if (st != BN_OK) return st;
+    prof_mark(c, "end");
+    BN_CUDA(cudaEventRecord(c->done, c->stream));
+    st = wait_done(c, opts);
+    if (st != BN_OK) return st;
+    fill_outputs(c, batch, k_eff, out);
+    if (c->profiling) {
+        size_t np = c->prof_names.size();
+        c->prof_ms.assign(np ? np - 1 : 0, 0.f);
+        for (size_t i = 0; i + 1 < np; ++i) cudaEventElapsedTime(&c->prof_ms[i], c->prof_events[i], c->prof_events[i + 1]);
     }
     return BN_OK;
 }

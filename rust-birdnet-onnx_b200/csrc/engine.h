@@ -94,6 +94,8 @@ struct bn_ctx {
     cudaEvent_t done = nullptr;
     float* h_in = nullptr;       // pinned [max_batch][S]
     float* d_in = nullptr;       // [max_batch][S]
+    int16_t* h_pcm = nullptr;    // pinned [max_batch * S] 16-bit PCM staging (bn_ctx_run_pcm16), allocated on first use
+    int16_t* d_pcm = nullptr;
     float* d_norm = nullptr;     // [max_batch][S] normalised audio (v2.4 front-end)
     uint32_t* d_minmax = nullptr;   // [max_batch][2] order-preserving keys of the per-segment min / max
     bool keep_normalized = true;   // write the FP32 normalised audio (tests: BN_KEEP_NORMALIZED=1; always in FP32 mode)
@@ -128,6 +130,8 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
 int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts,
                    bn_outputs* out);
 int ctx_enqueue_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, const bn_run_opts* opts);
+int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t first_pos, uint64_t step, uint64_t batch,
+                  const bn_run_opts* opts, bn_outputs* out);
 int ctx_wait(bn_ctx* c, const bn_run_opts* opts, bn_outputs* out);
 int fill_io_info(const Plan& plan, bn_io_info* out);
 }  // namespace bn

@@ -886,6 +886,38 @@ cudaError_t launch_se_rescale(PlanesPtr d, const float* gate, int batch, int npi
 }
 
 // ======================================================================================
+// CLI ingest on the device: 16-bit PCM -> FP32 / 32768 (read_wav,
+// src/bin/birdnet-analyze.rs:21, 684-687) and chunk_audio (707-743): segment b starts at sample
+// first_pos + b * step, samples past the end of the recording are zeros.  One thread = 4 samples.
+// ======================================================================================
+__global__ void __launch_bounds__(256) k_pcm16_to_segments(const int16_t* __restrict__ pcm, unsigned long long base,
+                                                           unsigned long long n_total, unsigned long long first_pos,
+                                                           unsigned long long step, float* __restrict__ out, int S) {
+    const int b = blockIdx.y;
+    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= S) return;
+    const unsigned long long pos = first_pos + (unsigned long long)b * step + (unsigned long long)i0;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long q = pos + j;
+        v[j] = (i0 + j < S && q < n_total) ? (float)__ldg(pcm + (q - base)) * (1.0f / 32768.0f) : 0.f;   // exact: power-of-two scale
+    }
+    float* dst = out + (size_t)b * S + i0;
+    if (i0 + 3 < S) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else for (int j = 0; j < 4 && i0 + j < S; ++j) dst[j] = v[j];
+}
+
+cudaError_t launch_pcm16_to_segments(const int16_t* pcm, uint64_t base, uint64_t n_total, uint64_t first_pos, uint64_t step,
+                                     float* out, int batch, int sample_count, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    if (sample_count & 3) return cudaErrorInvalidValue;          // float4 row alignment
+    dim3 grid((unsigned)((sample_count / 4 + 255) / 256), (unsigned)batch);
+    k_pcm16_to_segments<<<grid, 256, 0, stream>>>(pcm, base, n_total, first_pos, step, out, sample_count);
+    return cudaGetLastError();
+}
+
+// ======================================================================================
 // Stem: direct k x k conv for tiny Cin (the 2-channel spectrogram), planes in / planes out.
 // One thread per output pixel computes all Cout (<= 32) channels; weights live in smem.
 // ======================================================================================

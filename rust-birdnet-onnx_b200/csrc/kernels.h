@@ -27,6 +27,11 @@ cudaError_t launch_spectrogram_v24(const float* xnorm, const float* basis, int l
                                    int batch, int sample_count, int n_fft, int hop, int n_frames,
                                    int n_mels, int n_ch, int ch, float exponent, cudaStream_t stream);
 
+// ---- CLI ingest moved on-device (section 8f row 1): i16 PCM -> overlapping FP32 segments ------------
+// out[b][i] = pcm[first_pos + b*step + i - base] / 32768 (0 beyond n_total); `base` = recording index of pcm[0]
+cudaError_t launch_pcm16_to_segments(const int16_t* pcm, uint64_t base, uint64_t n_total, uint64_t first_pos, uint64_t step,
+                                     float* out, int batch, int sample_count, cudaStream_t stream);
+
 // ---- CNN (row A8) -----------------------------------------------------------------
 struct ConvParams {
     const float* in;        // [B][hin][win][cin]

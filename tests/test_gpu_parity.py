@@ -346,3 +346,30 @@ def test_device_pool_matches_single_context(v24_model_path, clf):
     assert emb is None and np.array_equal(logits, np.stack([r.raw_scores for r in res]))
     for i, r in enumerate(res):
         assert idx[i, :cnt[i]].tolist() == [p.index for p in r.predictions]
+
+
+@pytest.mark.gpu
+def test_pcm16_stream_matches_host_chunking(clf):
+    """bn_ctx_run_pcm16 (on-device i16 -> f32 / 32768 + chunk_audio) == the reference CLI's host-side
+    read_wav conversion + chunk_audio fed through predict_batch_with_context: bit-exact logits."""
+    from oracle import ingest_oracle as io
+    rng = np.random.default_rng(7)
+    S, sr = 144000, 48000
+    n = 5 * S + 12345                                             # ragged tail -> zero padding
+    t = np.arange(n, dtype=np.float64) / sr
+    pcm = (0.3 * np.sin(2 * np.pi * 1234.0 * t) * 32767 + rng.integers(-2000, 2000, n)).astype(np.int16)
+    ctx = clf.create_batch_context(4)                             # forces several calls per recording
+    for overlap in (0.0, 1.5):
+        got = clf.predict_pcm16_stream(ctx, pcm, overlap)
+        ref_segs = io.chunk_audio(io.pcm16_to_f32(pcm), S, overlap, sr)
+        assert len(got) == len(ref_segs) and len(got) >= 6
+        ref = []
+        for i in range(0, len(ref_segs), 4):
+            ref += clf.predict_batch_with_context(ctx, [s for _, s in ref_segs[i:i + 4]])
+        for (t0, r), (t1, _), rr in zip(got, ref_segs, ref):
+            assert t0 == t1
+            assert np.array_equal(r.raw_scores, rr.raw_scores)
+            assert [(p.index, p.confidence) for p in r.predictions] == [(p.index, p.confidence) for p in rr.predictions]
+    assert clf.predict_pcm16_stream(ctx, pcm, 3.0) == []          # step == 0 (birdnet-analyze.rs:721-724)
+    with pytest.raises(bb.Error):
+        clf.predict_pcm16_stream(ctx, np.zeros(0, dtype=np.int16))
