@@ -5,6 +5,7 @@
 // monitor), 676-727 (predict_batch), 826-867 (predict_batch_with_context);
 // src/batch_context.rs:102-133, 188-338.
 #include "engine.h"
+#include "hostcopy.h"
 
 #include <algorithm>
 #include <chrono>
@@ -909,7 +910,7 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
     if (T <= 1) {
         for (uint64_t ci = 0; ci < n_chunks; ++ci) {
             uint64_t lo = ci * chunk, hi = std::min(B, lo + chunk);
-            for (uint64_t i = lo; i < hi; ++i) memcpy(c->h_in + i * S, seg_ptrs[i], seg_bytes);   // batch_context.rs:209-211
+            for (uint64_t i = lo; i < hi; ++i) stream_copy(c->h_in + i * S, seg_ptrs[i], seg_bytes);   // batch_context.rs:209-211
             BN_CUDA(cudaMemcpyAsync(c->d_in + lo * S, c->h_in + lo * S, (hi - lo) * seg_bytes, cudaMemcpyHostToDevice, c->stream));
         }
         return BN_OK;
@@ -922,7 +923,7 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
             uint64_t ci = next.fetch_add(1);
             if (ci >= n_chunks) break;
             uint64_t lo = ci * chunk, hi = std::min(B, lo + chunk);
-            for (uint64_t i = lo; i < hi; ++i) memcpy(c->h_in + i * S, seg_ptrs[i], seg_bytes);
+            for (uint64_t i = lo; i < hi; ++i) stream_copy(c->h_in + i * S, seg_ptrs[i], seg_bytes);
             cudaError_t ce = cudaMemcpyAsync(c->d_in + lo * S, c->h_in + lo * S, (hi - lo) * seg_bytes, cudaMemcpyHostToDevice, c->stream);
             if (ce != cudaSuccess) err.store((int)ce);
         }
@@ -1001,7 +1002,7 @@ int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t fi
     const size_t piece = (size_t)4 << 20;                           // samples per pipelined copy (8 MiB)
     for (size_t o = 0; o < n; o += piece) {
         const size_t m = std::min(piece, n - o);
-        memcpy(c->h_pcm + o, pcm + first_pos + o, m * sizeof(int16_t));
+        stream_copy(c->h_pcm + o, pcm + first_pos + o, m * sizeof(int16_t));
         BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, c->h_pcm + o, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
     }
     BN_CUDA(launch_pcm16_to_segments(c->d_pcm, first_pos, n_samples, first_pos, step, c->d_in, (int)batch, (int)S, c->stream));
