@@ -627,6 +627,19 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             } else {
                 tp.out_f32 = c->d_tensor[op.out];
             }
+            // TMA-store epilogue: spatial outputs with >= 32 channels and no residual
+            static const bool no_out_tma = [] { const char* ev = getenv("BN_DISABLE_OUT_TMA"); return ev && ev[0] == '1'; }();
+            if (!no_out_tma && e->use_tma && is_spatial(p, op.out) && op.residual < 0 && (op.cout & 15) == 0 && op.cout >= 32) {
+                if (c->omap_state.empty()) { c->omaps.resize(p.ops.size()); c->omap_state.assign(p.ops.size(), 0); }
+                const uint8_t want = f32_rows ? 1 : 3;                   // the map depends on the output form
+                if (c->omap_state[i] != want && c->omap_state[i] != 2) {
+                    const uint64_t rows = (uint64_t)std::max<uint64_t>(c->max_batch, 1) * op.hout * op.wout;
+                    const bool ok = f32_rows ? tc_encode_out_tmap(&c->omaps[i], c->d_tensor[op.out], rows, (uint64_t)op.cout, true, 0)
+                                             : tc_encode_out_tmap(&c->omaps[i], tp.out_hi, rows, (uint64_t)op.cout, false, tp.out_plane);
+                    c->omap_state[i] = ok ? want : 2;
+                }
+                if (c->omap_state[i] == want) { tp.omap = c->omaps[i]; tp.out_tma = 1; }
+            }
             tp.wpack = d.wpack;
             tp.batch = B; tp.hin = op.hin; tp.win = op.win; tp.cin = op.cin;
             tp.hout = op.hout; tp.wout = op.wout; tp.cout = op.cout;

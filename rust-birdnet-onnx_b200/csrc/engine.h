@@ -103,6 +103,8 @@ struct bn_ctx {
     std::vector<float*> d_tensor;   // per plan tensor (aliases resolved to their root)
     std::vector<CUtensorMap> tmaps;   // per plan op: tensor map of its input planes (TC_IN_TMA layers), encoded on first use
     std::vector<uint8_t> tmap_state;  // 0 = not tried, 1 = ready, 2 = unavailable
+    std::vector<CUtensorMap> omaps;   // per plan op: tensor map of its output (TMA-store epilogue)
+    std::vector<uint8_t> omap_state;
     float* h_logits = nullptr;   // pinned
     float* h_emb = nullptr;      // pinned
     bn::Pred* d_topk = nullptr;

@@ -497,8 +497,14 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const uint32_t t_lane = tmem_base + a * 2u * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
             if (p.debug_flags & 2) {
             } else if (staged) {
+                const bool tma_out = p.out_tma != 0 && p.res_hi == nullptr && p.tiles_per_seg == p.m_tiles;
+                const bool f32_out = p.out_f32 != nullptr;
                 for (int c0 = cset * 32; c0 < NT; c0 += 32 * nsets) {
                     const int gw = NT - c0 < 32 ? 16 : 32;         // NT is a multiple of 16
+                    if (tma_out && gw != 32) {                      // the old path reuses the tile a TMA store may still be reading
+                        if (lane == 0) bulk_wait_group_read0();
+                        __syncwarp();
+                    }
                     for (int h = 0; h < gw; h += 16) {
                         uint32_t rm[16], rc[16];
                         __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
@@ -523,12 +529,44 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
                         }
+                        if (tma_out && gw == 32 && h == 0) {
+                            // the TMA engine may still be reading this warp's tile (previous block): wait right before the
+                            // first shared-memory store, after this block's TMEM loads and math are already done
+                            if (lane == 0) bulk_wait_group_read0();
+                            __syncwarp();
+                        }
+                        if (tma_out && gw == 32 && !f32_out) {
+                            // planes: split here (lane = row), fp16 tiles [hi|lo][32 rows][64 B], SWIZZLE_64B chunk order
+                            uint4 hq[2], lq[2];
+                            split8(v, hq[0], lq[0]);
+                            split8(v + 8, hq[1], lq[1]);
+                            uint8_t* t8 = reinterpret_cast<uint8_t*>(stg);
+                            const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+                            for (int j2 = 0; j2 < 2; ++j2) {
+                                const uint32_t cc = (uint32_t)((h >> 3) + j2) ^ sw;
+                                *reinterpret_cast<uint4*>(t8 + lane * 64 + (cc << 4)) = hq[j2];
+                                *reinterpret_cast<uint4*>(t8 + 2048 + lane * 64 + (cc << 4)) = lq[j2];
+                            }
+                        } else {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const int cc = (h >> 2) + j4;          // 16-byte chunk of the 32-column row
                             *reinterpret_cast<float4*>(stg + lane * 32 + ((cc ^ (lane & 7)) << 2)) =
                                 make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
                         }
+                        }
+                    }
+                    if (tma_out && gw == 32) {
+                        fence_proxy_async_smem();                  // generic-proxy tile writes -> visible to the TMA engine
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int row0 = sb * p.pix_per_seg + lp0;
+                            if (f32_out) tma_store_2d(&p.omap, stg, n_tile * NT + c0, row0);
+                            else tma_store_3d(&p.omap, stg, n_tile * NT + c0, row0, 0);
+                            bulk_commit_group();
+                        }
+                        continue;                                  // rows past M are clipped by the tensor map
                     }
                     __syncwarp();
                     const int osh = gw == 32 ? 2 : 1;              // log2(8-column octets per row)
@@ -618,6 +656,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[a]);
         }
+        if (p.out_tma != 0 && lane == 0) bulk_wait_group0();     // shared memory must outlive the engine's reads
         if (prof && warp == 5 && lane == 0) { p.prof[5] = pw0; p.prof[6] = (unsigned long long)(clock64() - prof_t0); }
     }
     tc_fence_before();
@@ -779,6 +818,37 @@ bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], 
         fprintf(stderr, "[bn] cuTensorMapEncodeTiled failed: CUresult %d (dims %llu %llu %llu %llu %llu, strides %llu %llu %llu %llu)\n", (int)r,
                 (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2], (unsigned long long)gd[3], (unsigned long long)gd[4],
                 (unsigned long long)gs[0], (unsigned long long)gs[1], (unsigned long long)gs[2], (unsigned long long)gs[3]);
+    return r == CUDA_SUCCESS;
+}
+
+bool tc_encode_out_tmap(CUtensorMap* out, void* base, uint64_t rows, uint64_t cout, bool f32, uint64_t plane_elems) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) != cudaSuccess || !sym) return false;
+        fn = reinterpret_cast<EncodeFn>(sym);
+    }
+    if (cout < 32 || rows == 0) return false;
+    CUresult r;
+    if (f32) {
+        const cuuint64_t gd[2] = {cout, rows};
+        const cuuint64_t gs[1] = {cout * 4};
+        const cuuint32_t bx[2] = {32, 32}, es[2] = {1, 1};
+        r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gd[3] = {cout, rows, 2};
+        const cuuint64_t gs[2] = {cout * 2, plane_elems * 2};
+        const cuuint32_t bx[3] = {32, 32, 2}, es[3] = {1, 1, 1};
+        r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS && getenv("BN_DEBUG")) fprintf(stderr, "[bn] output tensor map refused: CUresult %d (rows %llu cout %llu f32 %d)\n", (int)r,
+                                                         (unsigned long long)rows, (unsigned long long)cout, (int)f32);
     return r == CUDA_SUCCESS;
 }
 

@@ -21,6 +21,11 @@ struct TcConvParams {
     // TC_IN_TMA: 5-D tensor map (channel, x, y, segment, plane) over the input hi/lo planes; the A
     // tile of a K block is ONE cp.async.bulk.tensor per plane (zero fill outside the image = padding)
     alignas(64) CUtensorMap tmap;
+    // output tensor map (out_tma != 0): the epilogue warps hand their staged [32 rows][32 columns] tiles to the TMA
+    // engine instead of re-reading them and storing 16-byte pieces.  planes: 3-D (channel, row, plane) fp16, box
+    // {32,32,2}, SWIZZLE_64B; FP32 rows: 2-D (channel, row) f32, box {32,32}, SWIZZLE_128B.
+    alignas(64) CUtensorMap omap;
+    int out_tma;
     int kb;                  // channels per TMA box: 16 / 32 / 64 <-> SWIZZLE_32B / 64B / 128B
     int box_w, box_h;        // output pixels per tile row x rows per tile (box_w * box_h == 128), rect mode
     int flat;                // 1: A is a flat [M][K] matrix (1x1 stride-1 conv, front-end frames)
@@ -75,6 +80,8 @@ size_t tc_conv_halo_smem_bytes(int cin, int nt, int k_chunks, int slots, int epi
 // Encodes the 5-D (channel, x, y, segment, plane) fp16 tensor map; returns false if the driver refuses.
 bool tc_encode_tmap(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
                     const uint32_t box[5], const uint32_t elem_strides[5], int kb);
+// Encodes the output tensor map described at TcConvParams::omap; returns false if the driver refuses.
+bool tc_encode_out_tmap(CUtensorMap* out, void* base, uint64_t rows, uint64_t cout, bool f32, uint64_t plane_elems);
 void tc_pack_weights(const float* w, int K, int cout, int ldw, int nt, std::vector<uint16_t>& out,
                      int* n_tiles_out, int* k_chunks_out);
 
