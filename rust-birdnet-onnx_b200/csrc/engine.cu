@@ -629,7 +629,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             }
             // TMA-store epilogue: spatial outputs with >= 32 channels and no residual
             static const bool no_out_tma = [] { const char* ev = getenv("BN_DISABLE_OUT_TMA"); return ev && ev[0] == '1'; }();
-            if (!no_out_tma && e->use_tma && is_spatial(p, op.out) && op.residual < 0 && (op.cout & 15) == 0 && op.cout >= 32) {
+            if (!no_out_tma && e->use_tma && is_spatial(p, op.out) && (op.cout & 15) == 0 && op.cout >= 32) {
                 if (c->omap_state.empty()) { c->omaps.resize(p.ops.size()); c->omap_state.assign(p.ops.size(), 0); }
                 const uint8_t want = f32_rows ? 1 : 3;                   // the map depends on the output form
                 if (c->omap_state[i] != want && c->omap_state[i] != 2) {

@@ -497,7 +497,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const uint32_t t_lane = tmem_base + a * 2u * (uint32_t)NT + ((uint32_t)(q * 32) << 16);
             if (p.debug_flags & 2) {
             } else if (staged) {
-                const bool tma_out = p.out_tma != 0 && p.res_hi == nullptr && p.tiles_per_seg == p.m_tiles;
+                const bool tma_out = p.out_tma != 0 && p.tiles_per_seg == p.m_tiles;
                 const bool f32_out = p.out_f32 != nullptr;
                 for (int c0 = cset * 32; c0 < NT; c0 += 32 * nsets) {
                     const int gw = NT - c0 < 32 ? 16 : 32;         // NT is a multiple of 16
@@ -528,6 +528,21 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         } else if (p.act == KACT_SIGMOID) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+                        }
+                        if (tma_out && gw == 32 && p.res_hi != nullptr && row_ok) {
+                            // residual: this lane's row, 16 channels = one 32-byte sector per plane
+                            const size_t o = (size_t)row * p.cout + n;
+                            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + o);
+                            const uint4* rl = reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + o);
+#pragma unroll
+                            for (int j2 = 0; j2 < 2; ++j2) {
+                                const uint4 qh = __ldg(rh + j2), ql = __ldg(rl + j2);
+                                float fh[8], fl[8];
+                                unpack8(qh, fh);
+                                unpack8(ql, fl);
+#pragma unroll
+                                for (int e8 = 0; e8 < 8; ++e8) v[8 * j2 + e8] += fh[e8] + fl[e8];
+                            }
                         }
                         if (tma_out && gw == 32 && h == 0) {
                             // the TMA engine may still be reading this warp's tile (previous block): wait right before the
