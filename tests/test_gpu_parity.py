@@ -373,3 +373,48 @@ def test_pcm16_stream_matches_host_chunking(clf):
     assert clf.predict_pcm16_stream(ctx, pcm, 3.0) == []          # step == 0 (birdnet-analyze.rs:721-724)
     with pytest.raises(bb.Error):
         clf.predict_pcm16_stream(ctx, np.zeros(0, dtype=np.int16))
+
+
+@pytest.mark.gpu
+def test_cfg5_day_of_audio_sharded_with_range_filter(v24_model_path, clf, v24_spec):
+    """BASELINE config 5 at full size: 24 h of 48 kHz audio = 28,800 segments sharded over the visible GPUs
+    (DevicePool: contiguous whole-batch blocks, host gather in caller order, no collective) with the fused range
+    filter.  The oracle cannot run 28,800 segments in test time, so the full run is checked through
+    size-independent properties: the stream cycles through 320 distinct synthetic segments, every repetition
+    must reproduce the single-context result for that segment bit for bit, and the fused filter must equal the
+    reference's post-filter (rangefilter.rs:527-579 semantics) on every one of them."""
+    from birdnet_b200.multi_gpu import DevicePool
+    from birdnet_b200.rangefilter import dense_range_state
+    from oracle import postprocess_oracle as po
+    n_total, n_distinct = 28_800, 320
+    base = synth.batch(0, n_distinct, 144000, 48000)
+    labels = clf.labels()
+    loc_all = po.mock_embeddings(v24_spec.num_species, 5)
+    loc = [bb.LocationScore(labels[i], float(loc_all[i]), i) for i in range(len(labels)) if loc_all[i] >= 0.0 or i % 2]
+    thr = 0.01                                                    # rangefilter.rs:165 default
+    # single-context ground truth for the 320 distinct segments (itself checked against the oracle elsewhere)
+    ctx = clf.create_batch_context(64)
+    plain = []
+    for i in range(0, n_distinct, 64):
+        plain += clf.predict_batch_with_context(ctx, list(base[i:i + 64]))
+    rf = bb.RangeFilter.from_labels(labels, threshold=thr)
+    want = rf.filter_batch_predictions([r.predictions for r in plain], loc, True)
+    n_dev = _ffi.lib.bn_device_count()
+    ids = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    pool = DevicePool(v24_model_path, ids, ctx_batch=256)
+    pool.set_postprocess(5, 0.1)
+    state, score = dense_range_state(labels, loc, thr)
+    pool.set_range_filter(state, score, True)
+    order = (np.arange(n_total) * 7) % n_distinct                 # 7 is coprime to 320: every segment repeats 90 times
+    ref_logits = np.stack([r.raw_scores for r in plain])
+    done = 0
+    for lo in range(0, n_total, 3200):                            # 9 pool calls of 3,200 segments (12.5 batches each: ragged)
+        sel = order[lo:lo + 3200]
+        logits, emb, idx, conf, cnt = pool.run([base[j] for j in sel])
+        assert emb is None and np.array_equal(logits, ref_logits[sel])
+        for row, j in enumerate(sel):
+            w = want[j]
+            assert idx[row, :cnt[row]].tolist() == [p.index for p in w]
+            assert np.allclose(conf[row, :cnt[row]], [p.confidence for p in w], atol=1e-7)
+        done += len(sel)
+    assert done == n_total
