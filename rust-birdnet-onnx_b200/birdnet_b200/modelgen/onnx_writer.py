@@ -253,11 +253,11 @@ def build_model_bytes(spec: GraphSpec, weights: Dict[str, np.ndarray] = None) ->
 
 def write_model(spec: GraphSpec, path: str, weights: Dict[str, np.ndarray] = None) -> None:
     data = build_model_bytes(spec, weights)
-    tmp = path + ".tmp"
+    import os
+    tmp = f"{path}.{os.getpid()}.tmp"          # several ranks may generate the same (deterministic) file at once
     with open(tmp, "wb") as f:
         f.write(data)
-    import os
-    os.replace(tmp, path)
+    os.replace(tmp, path)                      # atomic: readers see either no file or the complete one
 
 
 # ---------------------------------------------------------------- parsing (tests / tools)
