@@ -40,12 +40,14 @@ for s in stages:
     launch_stage += [s] * (3 if s == "normalize" else 1)
 
 out_rows, traffic = [], {}
+t_unit = units[col["gpu__time_duration.sum"]]
+t_scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(t_unit, 1.0)      # -> microseconds
 ur, uw = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
 for i, r in enumerate(data):
     st = launch_stage[i] if i < len(launch_stage) else "?"
     rd, wr = to_bytes(f(r, "dram__bytes_read.sum"), ur), to_bytes(f(r, "dram__bytes_write.sum"), uw)
     traffic[st] = traffic.get(st, 0.0) + rd + wr
-    out_rows.append((i, st, r[col["Kernel Name"]].split("(")[0][:34], f(r, "gpu__time_duration.sum"), rd / 1e6, wr / 1e6,
+    out_rows.append((i, st, r[col["Kernel Name"]].split("(")[0][:34], f(r, "gpu__time_duration.sum") * t_scale, rd / 1e6, wr / 1e6,
                      f(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
                      f(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                      f(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
