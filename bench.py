@@ -305,30 +305,40 @@ def run_ours(args):
     value = world * B * K / (dev_ms * 1e-3)
 
     # ---- e2e: public API with host slices, `depth` contexts driven by `depth` host threads ------
+    # headline: the caller keeps its segments in page-locked host memory (bb.pinned_array -> bn_host_alloc), so
+    # the engine DMAs them in place; `e2e_pageable`: ordinary numpy memory, gathered into the engine's pinned slab
     depth = max(1, args.pipeline_depth)
     ctxs = [ctx] + [clf.create_batch_context(B) for _ in range(depth - 1)]
-    for c in ctxs:
-        for _ in range(2):
-            clf.predict_batch_with_context(c, segs)
-    n_e2e = depth * max(4, -(-K // depth))               # whole rounds: every thread drives the same number of batches
-    sink = [0] * depth
+    pinned = bb.pinned_array(audio.shape)
+    pinned[:] = audio
+    segs_pinned = list(pinned)
+    n_e2e = depth * max(8, -(-K // depth))               # whole rounds: every thread drives the same number of batches
 
-    def e2e_worker(t):
-        for i in range(t, n_e2e, depth):
-            res = clf.predict_batch_with_context(ctxs[t], segs)
-            sink[t] += len(res[0].predictions) + len(res)
-    barrier()
-    t0 = time.perf_counter()
-    th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(depth)]
-    [x.start() for x in th]
-    [x.join() for x in th]
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * n_e2e / e2e_s
+    def run_e2e(seg_list):
+        for c in ctxs:
+            for _ in range(2):
+                clf.predict_batch_with_context(c, seg_list)
+        sink = [0] * depth
+
+        def e2e_worker(t):
+            for i in range(t, n_e2e, depth):
+                res = clf.predict_batch_with_context(ctxs[t], seg_list)
+                sink[t] += len(res[0].predictions) + len(res)
+        barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(depth)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * B * n_e2e / dt
+
+    e2e_value = run_e2e(segs_pinned)
+    e2e_pageable = run_e2e(segs)
     h2d = B * 144000 * 4
     d2h = B * spec.num_species * 4 + B * 5 * 8 + B * 4
 
@@ -337,7 +347,8 @@ def run_ours(args):
     ingest = None
     if not args.no_ingest:
         n_b = 4                                                   # batches per recording
-        pcm = np.tile((np.clip(audio.reshape(-1), -1.0, 1.0) * 32767.0).astype(np.int16), n_b)
+        pcm = bb.pinned_array((n_b * B * 144000,), np.int16)      # the recording sits in page-locked host memory
+        pcm[:] = np.tile((np.clip(audio.reshape(-1), -1.0, 1.0) * 32767.0).astype(np.int16), n_b)
         for c in ctxs:
             clf.predict_pcm16_stream(c, pcm[: B * 144000])
         got = [0] * depth
@@ -399,7 +410,10 @@ def run_ours(args):
                        "parallelism": f"{world} independent per-GPU shards, no collective",
                        "precision_policy": "FP32-equivalent (see DESIGN.md)",
                        "e2e_pipeline_depth": depth, "host_cores": os.cpu_count(), "host_pack_threads_per_call": pack_threads},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "inputs": "256 host slices per step in page-locked host memory (bn_host_alloc), copied to the GPU in place"},
+            "e2e_pageable": {"value": e2e_pageable, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                             "inputs": "256 pageable host slices per step, gathered into the engine's pinned slab first"},
             "ingest_pcm16": ingest,
             "gpu_launches": int(launches_per_step * K),
             "clocks": clocks,

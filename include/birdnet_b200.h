@@ -198,6 +198,12 @@ int bn_pool_run(bn_pool* pool, const float* const* seg_ptrs, const uint64_t* seg
                 const bn_run_opts* opts, float* logits, float* embeddings, bn_pred* topk, uint32_t* topk_count,
                 uint64_t topk_stride);
 int bn_device_count(void);
+/* Page-locked host memory for callers that want their segments DMA-able in place: when every segment pointer
+ * handed to bn_ctx_run / bn_engine_run lies in page-locked host memory (from here, cudaHostAlloc or
+ * cudaHostRegister), the engine skips the gather into its own staging slab (the memcpy of
+ * batch_context.rs:199-211) and copies host -> device straight from the caller's slices. */
+void* bn_host_alloc(uint64_t bytes);
+void bn_host_free(void* p);
 
 #ifdef __cplusplus
 }

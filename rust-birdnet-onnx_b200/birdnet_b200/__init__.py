@@ -8,6 +8,6 @@ from .errors import (AudioFormat, AudioRead, BatchInputSize, Cancelled, Error, I
 from .types import (ExecutionProviderInfo, LabelFormat, LocationScore, ModelConfig, ModelType,  # noqa: F401
                     Prediction, PredictionResult, available_execution_providers)
 from .inference_options import CancellationToken, InferenceOptions  # noqa: F401
-from .classifier import BatchInferenceContext, Classifier, ClassifierBuilder  # noqa: F401
+from .classifier import BatchInferenceContext, Classifier, ClassifierBuilder, pinned_array  # noqa: F401
 from .rangefilter import (RangeFilter, RangeFilterBuilder, calculate_week,  # noqa: F401
                           validate_coordinates, validate_date)

@@ -109,6 +109,8 @@ SIGNATURES = {
     "bn_pool_run": (C.c_int, [_vp, _P(_vp), _P(C.c_uint64), C.c_uint64, _P(RunOpts), _P(C.c_float),
                               _P(C.c_float), _P(Pred), _P(C.c_uint32), C.c_uint64]),
     "bn_device_count": (C.c_int, []),
+    "bn_host_alloc": (C.c_void_p, [C.c_uint64]),
+    "bn_host_free": (None, [C.c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

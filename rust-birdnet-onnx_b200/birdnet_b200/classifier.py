@@ -148,6 +148,38 @@ class ClassifierBuilder:
                           info)
 
 
+class _PinnedBlock:
+    """Owner of one bn_host_alloc block (freed when the last array view dies)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = _lib.bn_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"bn_host_alloc({nbytes}) failed")
+        self.nbytes = nbytes
+
+    def __del__(self):
+        p, self.ptr = getattr(self, "ptr", None), None
+        if p:
+            _lib.bn_host_free(p)
+
+
+def pinned_array(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array in page-locked host memory (bn_host_alloc): segments that live here are copied to the GPU in
+    place by predict_batch / predict_batch_with_context, without the gather into the engine's staging slab."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _PinnedBlock(max(n, 1))
+    buf = (C.c_char * blk.nbytes).from_address(blk.ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    _PINNED_OWNERS[id(buf)] = blk
+    import weakref
+    weakref.finalize(buf, _PINNED_OWNERS.pop, id(buf), None)
+    return arr
+
+
+_PINNED_OWNERS = {}
+
+
 class BatchInferenceContext:
     """src/batch_context.rs:70-339: pinned input slab + device slabs + streams, reused."""
 

@@ -15,6 +15,13 @@ void bn_last_error_detail(uint64_t out[3]) {
 }
 const char* bn_version(void) { return "birdnet_b200 0.1.0 (sm_100a)"; }
 
+void* bn_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void bn_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int bn_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -917,6 +917,30 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
     bn_engine* e = c->eng;
     const size_t S = (size_t)e->plan.sample_count;
     const size_t seg_bytes = S * sizeof(float);
+    // segments already in page-locked host memory: DMA straight from the caller's slices, contiguous runs as one copy
+    {
+        bool all_pinned = true;
+        for (uint64_t i = 0; i < B && all_pinned; ++i) {
+            cudaPointerAttributes at{};
+            const cudaError_t ce = cudaPointerGetAttributes(&at, seg_ptrs[i]);
+            if (ce != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
+            // the last byte must be page-locked too (a slice may straddle the end of a registered range)
+            cudaPointerAttributes at2{};
+            const cudaError_t ce2 = cudaPointerGetAttributes(&at2, reinterpret_cast<const char*>(seg_ptrs[i]) + seg_bytes - 1);
+            if (ce2 != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
+            all_pinned = at.type == cudaMemoryTypeHost && at2.type == cudaMemoryTypeHost;
+        }
+        if (all_pinned) {
+            uint64_t i = 0;
+            while (i < B) {
+                uint64_t j = i + 1;
+                while (j < B && seg_ptrs[j] == seg_ptrs[j - 1] + S && (j - i) < 32) ++j;     // <= 32 segments (18 MB) per copy: the kernels can start early
+                BN_CUDA(cudaMemcpyAsync(c->d_in + i * S, seg_ptrs[i], (j - i) * seg_bytes, cudaMemcpyHostToDevice, c->stream));
+                i = j;
+            }
+            return BN_OK;
+        }
+    }
     const uint64_t chunk = 8;
     const uint64_t n_chunks = (B + chunk - 1) / chunk;
     int T = (int)std::min<uint64_t>((uint64_t)e->pack_threads, n_chunks);
@@ -1012,11 +1036,20 @@ int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t fi
     const uint64_t hi = std::min<uint64_t>(n_samples, first_pos + (batch - 1) * step + S);
     const size_t n = (size_t)(hi - first_pos);                      // <= (batch-1)*step + S <= max_batch * S
     prof_mark(c, "h2d");
+    bool pinned = false;                                            // recording already page-locked: DMA in place
+    {
+        cudaPointerAttributes a0{}, a1{};
+        if (cudaPointerGetAttributes(&a0, pcm + first_pos) == cudaSuccess && cudaPointerGetAttributes(&a1, pcm + first_pos + n - 1) == cudaSuccess)
+            pinned = a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+        else
+            cudaGetLastError();
+    }
     const size_t piece = (size_t)4 << 20;                           // samples per pipelined copy (8 MiB)
     for (size_t o = 0; o < n; o += piece) {
         const size_t m = std::min(piece, n - o);
-        stream_copy(c->h_pcm + o, pcm + first_pos + o, m * sizeof(int16_t));
-        BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, c->h_pcm + o, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+        const int16_t* src = pcm + first_pos + o;
+        if (!pinned) { stream_copy(c->h_pcm + o, src, m * sizeof(int16_t)); src = c->h_pcm + o; }
+        BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, src, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
     }
     BN_CUDA(launch_pcm16_to_segments(c->d_pcm, first_pos, n_samples, first_pos, step, c->d_in, (int)batch, (int)S, c->stream));
     st = enqueue_forward(c, c->d_in, (int)batch, post, k_eff);

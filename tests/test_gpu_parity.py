@@ -418,3 +418,24 @@ def test_cfg5_day_of_audio_sharded_with_range_filter(v24_model_path, clf, v24_sp
             assert np.allclose(conf[row, :cnt[row]], [p.confidence for p in w], atol=1e-7)
         done += len(sel)
     assert done == n_total
+
+
+@pytest.mark.gpu
+def test_pinned_segments_skip_the_gather_and_match(clf):
+    """Segments that live in page-locked host memory (bn_host_alloc) are DMA'd in place; results are bit-identical
+    to the gather path, for contiguous rows, permuted rows and a mix of pinned and pageable slices."""
+    B = 24
+    audio = synth.batch(3, B, 144000, 48000)
+    ctx = clf.create_batch_context(B)
+    ref = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, list(audio))])
+    pinned = bb.pinned_array(audio.shape)
+    pinned[:] = audio
+    got = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, list(pinned))])
+    assert np.array_equal(got, ref)
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(B)
+    got_p = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, [pinned[j] for j in perm])])
+    assert np.array_equal(got_p, ref[perm])
+    mixed = [pinned[j] if j % 2 else audio[j] for j in range(B)]          # falls back to the gather path
+    got_m = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, mixed)])
+    assert np.array_equal(got_m, ref)
+    assert np.array_equal(np.stack([r.raw_scores for r in clf.predict_batch(list(pinned[:5]))]), ref[:5])
