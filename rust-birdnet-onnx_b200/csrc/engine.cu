@@ -741,6 +741,7 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
             tp.m_tiles = (tp.M + 127) / 128;
             tp.pix_stride = ft.row_stride; tp.seg_stride = ft.rows * ft.row_stride; tp.tab_cin = ft.K;
             tp.nt = ft.nt; tp.stages = ft.stages; tp.tmem_cols = ft.tmem_cols;
+            tp.prof = c->profiling && getenv("BN_TC_PROFILE") ? tc_conv_prof_slot(120 + (int)bi) : nullptr;
             BN_CUDA(launch_tc_conv(tp, e->num_sms, s));
         } else if (e->tc_mode)
             BN_CUDA(launch_spectrogram_v24_planes(fe_in, e->d_basis[bi], e->ldb[bi], planes_of(c, p.fe.out_tensor), B, p.sample_count,

@@ -771,7 +771,15 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
     // two co-resident CTAs per SM when shared memory, TMEM (512 columns) and registers allow it
     const int per_sm = (p.in_mode == TC_IN_PLANES && two_per_sm(p.nt, p.stages)) ? 2 : 1;
     const int epi_warps = per_sm == 2 ? 4 : resolve_epi_warps(p.epi_warps);
-    const size_t smem = tc_conv_smem_bytes(p.nt, p.stages, epi_warps);
+    size_t smem = tc_conv_smem_bytes(p.nt, p.stages, epi_warps);
+    if (p.spec_nframes > 0 && per_sm == 1 && p.in_mode == TC_IN_PLANES) {
+        // the spectrogram epilogue stores straight from registers: no staging tiles, so the whole budget goes to the
+        // operand ring (this GEMM streams ~2 MB per tile through it and is bound by the bytes in flight per SM)
+        const size_t stage_b = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)p.nt * 128;
+        int st = (int)((SMEM_ONE_PER_SM - 1024) / stage_b);
+        if (st > MAX_STAGES) st = MAX_STAGES;
+        if (st > p.stages) { p.stages = st; smem = 1024 + (size_t)st * stage_b; }
+    }
     if (smem > SMEM_ONE_PER_SM) return cudaErrorInvalidValue;
     const int slots = num_sms * per_sm;
     dim3 grid((unsigned)(total < slots ? total : slots));
