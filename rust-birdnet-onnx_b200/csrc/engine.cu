@@ -348,6 +348,8 @@ bn_ctx::~bn_ctx() {
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_results) cudaEventDestroy(ev_results);
+    if (ev_fetched) cudaEventDestroy(ev_fetched);
 }
 
 namespace bn {
@@ -365,6 +367,8 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     BN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     BN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     BN_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    BN_CUDA(cudaEventCreateWithFlags(&c->ev_results, cudaEventDisableTiming));
+    BN_CUDA(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
     BN_CUDA(cudaHostAlloc(&c->h_in, mb * S * sizeof(float), cudaHostAllocDefault));
     memset(c->h_in, 0, mb * S * sizeof(float));    // vec![0.0f32; max*sample_count], batch_context.rs:122
     BN_CUDA(cudaMalloc(&c->d_in, mb * S * sizeof(float)));
@@ -429,6 +433,7 @@ static inline PlanesPtr planes_of(bn_ctx* c, int t) {
 }
 
 static void prof_mark(bn_ctx* c, const char* name);
+static int wait_for_fetch(bn_ctx* c);
 
 // squeeze-excite tail starting at op i?  (FC silu -> FC sigmoid -> conv gated by it, input = the
 // tensor whose pool feeds the first FC).  Returns the index of the gated conv or -1.
@@ -515,6 +520,12 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
     for (size_t i = 0; i < p.ops.size(); ++i) {
         const PlanOp& op = p.ops[i];
         const DevOp& d = e->dev_ops[i];
+        // the previous run's results may still be on their way to the host: wait before overwriting them
+        if (c->fetch_pending && op.out >= 0 &&
+            (p.root(op.out) == p.root(p.logits_tensor) || (p.embedding_tensor >= 0 && p.root(op.out) == p.root(p.embedding_tensor)))) {
+            const int ws = wait_for_fetch(c);
+            if (ws != BN_OK) return ws;
+        }
         if (op.kind == OP_LINEAR && (int)i == fused_se_fc) {
             prescaled_conv = match_se_tail(p, i);
             ++i;                                 // both FCs ran inside launch_dw_se
@@ -775,6 +786,7 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     }
     }
     prof_mark(c, "topk_epilogue");
+    { const int ws = wait_for_fetch(c); if (ws != BN_OK) return ws; }     // top-k slots and counts are fetched too
     TopkParams tp{};
     tp.logits = c->d_tensor[p.logits_tensor];
     tp.batch = B;
@@ -794,14 +806,39 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     return BN_OK;
 }
 
+// Results leave on the copy stream, so the next batch's kernels (same compute stream) start while the 6.7 MB of
+// logits are still crossing PCIe; the compute stream only waits for that copy right before it overwrites the result
+// buffers again (wait_for_fetch, called in front of the first op that writes an output tensor).
 static int enqueue_fetch(bn_ctx* c, int B, uint64_t k_eff) {
     const Plan& p = c->eng->plan;
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->profiling ? c->stream : c->copy_stream;      // profiling keeps everything on one timeline
+    if (!c->profiling) {
+        BN_CUDA(cudaEventRecord(c->ev_results, c->stream));
+        BN_CUDA(cudaStreamWaitEvent(s, c->ev_results, 0));
+    }
     BN_CUDA(cudaMemcpyAsync(c->h_logits, c->d_tensor[p.logits_tensor], (size_t)B * p.num_species * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (p.embedding_tensor >= 0)
         BN_CUDA(cudaMemcpyAsync(c->h_emb, c->d_tensor[p.embedding_tensor], (size_t)B * p.embedding_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (k_eff > 0) BN_CUDA(cudaMemcpyAsync(c->h_topk, c->d_topk, (size_t)B * k_eff * sizeof(Pred), cudaMemcpyDeviceToHost, s));
     BN_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, (size_t)B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (!c->profiling) {
+        BN_CUDA(cudaEventRecord(c->ev_fetched, s));
+        c->fetch_pending = true;
+    }
+    return BN_OK;
+}
+
+// the `done` event of a run: after the fetch when there is one
+static int record_done(bn_ctx* c, bool fetched) {
+    BN_CUDA(cudaEventRecord(c->done, (fetched && !c->profiling) ? c->copy_stream : c->stream));
+    return BN_OK;
+}
+
+static int wait_for_fetch(bn_ctx* c) {
+    if (c->fetch_pending) {
+        BN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fetched, 0));
+        c->fetch_pending = false;
+    }
     return BN_OK;
 }
 
@@ -854,6 +891,7 @@ static int begin_run(bn_ctx* c, PostCfg& post, uint64_t& k_eff, const bn_run_opt
     BN_CUDA(cudaSetDevice(e->device));
     if (c->draining) {                       // a timed-out / cancelled run may still be in flight
         BN_CUDA(cudaStreamSynchronize(c->stream));
+        BN_CUDA(cudaStreamSynchronize(c->copy_stream));
         c->draining = false;
     }
     {
@@ -885,7 +923,8 @@ int ctx_enqueue_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fet
     if (st != BN_OK) return st;
     if (fetch) { st = enqueue_fetch(c, (int)batch, k_eff); if (st != BN_OK) return st; }
     prof_mark(c, "end");
-    BN_CUDA(cudaEventRecord(c->done, c->stream));
+    st = record_done(c, fetch);
+    if (st != BN_OK) return st;
     c->pending_batch = batch;
     c->pending_k = k_eff;
     return BN_OK;
@@ -1000,7 +1039,8 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
     st = enqueue_fetch(c, (int)batch, k_eff);
     if (st != BN_OK) return st;
     prof_mark(c, "end");
-    BN_CUDA(cudaEventRecord(c->done, c->stream));
+    st = record_done(c, true);
+    if (st != BN_OK) return st;
     st = wait_done(c, opts);
     if (st != BN_OK) return st;
     fill_outputs(c, batch, k_eff, out);
@@ -1059,7 +1099,8 @@ int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t fi
     st = enqueue_fetch(c, (int)batch, k_eff);
     if (st != BN_OK) return st;
     prof_mark(c, "end");
-    BN_CUDA(cudaEventRecord(c->done, c->stream));
+    st = record_done(c, true);
+    if (st != BN_OK) return st;
     st = wait_done(c, opts);
     if (st != BN_OK) return st;
     fill_outputs(c, batch, k_eff, out);

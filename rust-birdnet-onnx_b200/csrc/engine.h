@@ -92,6 +92,9 @@ struct bn_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t ev_results = nullptr;   // compute stream: logits / top-k of this run are final
+    cudaEvent_t ev_fetched = nullptr;   // copy stream: the previous run's results have left the device buffers
+    bool fetch_pending = false;
     float* h_in = nullptr;       // pinned [max_batch][S]
     float* d_in = nullptr;       // [max_batch][S]
     int16_t* h_pcm = nullptr;    // pinned [max_batch * S] 16-bit PCM staging (bn_ctx_run_pcm16), allocated on first use
