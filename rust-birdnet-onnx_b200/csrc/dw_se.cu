@@ -68,8 +68,11 @@ __host__ __device__ inline size_t dw_per_channel_floats(int hin, int win, int pa
     return (f32in ? 2 * patch : patch + (size_t)hin * win) + 2 * (size_t)(k * k + 1);
 }
 
+#ifndef BN_DW_MINB
+#define BN_DW_MINB 2
+#endif
 template <int K, int S, int XB, int YB, int CG_SHIFT, bool F32IN>
-__global__ void __launch_bounds__(DW_THREADS, 2) k_dw_se(const DwSeParams p) {
+__global__ void __launch_bounds__(DW_THREADS, BN_DW_MINB) k_dw_se(const DwSeParams p) {
     constexpr int cg_shift = CG_SHIFT;
     extern __shared__ __align__(16) float smem_dw[];
     constexpr int NCOL = (XB - 1) * S + K;
@@ -201,20 +204,26 @@ __global__ void __launch_bounds__(DW_THREADS, 2) k_dw_se(const DwSeParams p) {
 #pragma unroll
                 for (int j = 0; j < XB; ++j) acc[y][j] = bias;
             const float* base = patch + (((size_t)(oy0 * S) * wp + ox0 * S) << cg_shift) + 2 * cp;
+            // every staged value is loaded once and scattered into all the outputs of the block it touches:
+            // (NROW x NCOL) 64-bit shared-memory reads for XB*YB*K*K packed FMAs - shared-memory bandwidth is the most
+            // utilised resource of this loop, so taller / wider blocks are what make it faster
 #pragma unroll
             for (int r = 0; r < NROW; ++r) {
-                unsigned long long col[NCOL];
                 const float* rowp = base + (size_t)(r * wp) * CG;
 #pragma unroll
-                for (int x = 0; x < NCOL; ++x) col[x] = *reinterpret_cast<const unsigned long long*>(rowp + x * CG);
+                for (int x = 0; x < NCOL; ++x) {
+                    const unsigned long long v = *reinterpret_cast<const unsigned long long*>(rowp + x * CG);
 #pragma unroll
-                for (int y = 0; y < YB; ++y) {
-                    const int ky = r - y * S;
-                    if (ky < 0 || ky >= K) continue;
+                    for (int y = 0; y < YB; ++y) {
+                        const int ky = r - y * S;
+                        if (ky < 0 || ky >= K) continue;
 #pragma unroll
-                    for (int j = 0; j < XB; ++j)
-#pragma unroll
-                        for (int kx = 0; kx < K; ++kx) acc[y][j] = ffma2(col[j * S + kx], w[ky * K + kx], acc[y][j]);
+                        for (int j = 0; j < XB; ++j) {
+                            const int kx = x - j * S;
+                            if (kx < 0 || kx >= K) continue;
+                            acc[y][j] = ffma2(v, w[ky * K + kx], acc[y][j]);
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) k_dw_se(const DwSeParams p) {
     }
 }
 
-constexpr size_t DW_SE_SMEM_TWO = 113 * 1024;      // two CTAs per SM
+constexpr size_t DW_SE_SMEM_TWO = (BN_DW_MINB >= 3 ? 74 : 113) * 1024;      // BN_DW_MINB CTAs per SM
 constexpr size_t DW_SE_SMEM_MAX = 220 * 1024;
 
 template <int K, int S, int XB, int YB, bool F32IN>
@@ -351,21 +360,26 @@ cudaError_t set_attr_one() {
     return e;
 }
 
-// pixel blocks: 3-row maps take a whole column per thread (1 x 3); wider maps 4 (stride 1) or 2 (stride 2) pixels of a row
+// pixel blocks (XB x YB outputs per thread): stride 1 -> 4x3, 2x3, 4x1, 1x3; stride 2 -> 2x3, 2x1, 1x3.  The 4x3 / 2x3
+// blocks exist only for the FP32 hand-off input.
 template <int K, int S>
 cudaError_t set_attr_ks() {
     cudaError_t e = set_attr_one<K, S, 1, 3, true>();
     if (e == cudaSuccess) e = set_attr_one<K, S, 1, 3, false>();
     if (e == cudaSuccess) e = set_attr_one<K, S, S == 1 ? 4 : 2, 1, true>();
     if (e == cudaSuccess) e = set_attr_one<K, S, S == 1 ? 4 : 2, 1, false>();
+    if (e == cudaSuccess) e = set_attr_one<K, S, 2, 3, true>();
+    if (e == cudaSuccess && S == 1) e = set_attr_one<K, S, 4, 3, true>();
     return e;
 }
 
 template <int K, int S>
 cudaError_t launch_ks(const DwSeParams& p, int xb, int yb, int cg_shift, size_t smem, cudaStream_t stream) {
     const bool f32 = p.in_f32 != nullptr;
-    if (yb == 3) return f32 ? launch_one<K, S, 1, 3, true>(p, cg_shift, smem, stream) : launch_one<K, S, 1, 3, false>(p, cg_shift, smem, stream);
-    if (xb == (S == 1 ? 4 : 2))
+    if (f32 && yb == 3 && xb == 4 && S == 1) return launch_one<K, S, 4, 3, true>(p, cg_shift, smem, stream);
+    if (f32 && yb == 3 && xb == 2) return launch_one<K, S, 2, 3, true>(p, cg_shift, smem, stream);
+    if (yb == 3 && xb == 1) return f32 ? launch_one<K, S, 1, 3, true>(p, cg_shift, smem, stream) : launch_one<K, S, 1, 3, false>(p, cg_shift, smem, stream);
+    if (yb == 1 && xb == (S == 1 ? 4 : 2))
         return f32 ? launch_one<K, S, S == 1 ? 4 : 2, 1, true>(p, cg_shift, smem, stream) : launch_one<K, S, S == 1 ? 4 : 2, 1, false>(p, cg_shift, smem, stream);
     return cudaErrorInvalidValue;
 }
@@ -376,29 +390,37 @@ cudaError_t launch_ks(const DwSeParams& p, int xb, int yb, int cg_shift, size_t 
 static bool dw_se_config(const DwSeParams& p, int* xb, int* yb, int* cg_shift, size_t* smem) {
     if ((p.k != 3 && p.k != 5) || (p.stride != 1 && p.stride != 2) || p.pad != p.k / 2 || (p.c & 15) || p.act != KACT_SILU) return false;
     if (p.r < 1 || p.r > 256 || p.batch <= 0) return false;
-    if (p.hout == 3) { *xb = 1; *yb = 3; }
-    else if (p.stride == 1 && (p.wout % 4) == 0) { *xb = 4; *yb = 1; }
-    else if (p.stride == 2 && (p.wout % 2) == 0) { *xb = 2; *yb = 1; }
-    else return false;
     const bool f32 = p.in_f32 != nullptr;
-    const int nblk = (p.hout / *yb) * (p.wout / *xb);
     const size_t per_ch = dw_per_channel_floats(p.hin, p.win, p.pad, p.k, f32) * sizeof(float);
     const size_t fixed = dw_fixed_floats(p.c, p.r) * sizeof(float);
-    int best = -1;
-    double best_score = 0.0;
-    for (int sh = 6; sh >= 3; --sh) {                       // CG = 64, 32, 16, 8
-        const int cg = 1 << sh;
-        if (p.c % cg) continue;
-        const size_t bytes = fixed + per_ch * cg;
-        if (bytes > DW_SE_SMEM_MAX) continue;
-        const int pgn = DW_THREADS / (cg / 2);
-        const double util = (double)nblk / (double)(((nblk + pgn - 1) / pgn) * pgn);
-        const double score = util * (bytes <= DW_SE_SMEM_TWO ? 1.0 : 0.6);      // one CTA per SM hides far less latency
-        if (score > best_score + 1e-9) { best_score = score; best = sh; }
+    static const int force = [] { const char* ev = getenv("BN_DW_SHAPE"); return ev ? atoi(ev) : 0; }();     // e.g. 41, 43, 23, 13, 21
+    const int shapes[5][2] = {{4, 3}, {2, 3}, {4, 1}, {2, 1}, {1, 3}};
+    double best_cost = 1e30;
+    int bx = 0, by = 0, bsh = -1;
+    for (auto& sh2 : shapes) {
+        const int x = sh2[0], y = sh2[1];
+        if (force && force != x * 10 + y) continue;
+        if ((x == 4 && p.stride != 1) || (x == 2 && y == 1 && p.stride != 2)) continue;       // instantiated combinations only
+        if ((x * y > 4 || (x == 2 && y == 3)) && !f32) continue;
+        if (p.wout % x || p.hout % y) continue;
+        const int nblk = (p.hout / y) * (p.wout / x);
+        // cost per output: 64-bit shared-memory reads (2 LSU cycles per warp each, one LSU per SM) + packed FMAs (2 cycles on one of 4 pipes)
+        const int nrow = (y - 1) * p.stride + p.k, ncol = (x - 1) * p.stride + p.k;
+        const double per_out = 2.0 * nrow * ncol / (x * y) + 0.5 * p.k * p.k + 6.0;
+        for (int sh = 6; sh >= 3; --sh) {                   // CG = 64, 32, 16, 8
+            const int cg = 1 << sh;
+            if (p.c % cg) continue;
+            const size_t bytes = fixed + per_ch * cg;
+            if (bytes > DW_SE_SMEM_MAX) continue;
+            const int pgn = DW_THREADS / (cg / 2);
+            const double util = (double)nblk / (double)(((nblk + pgn - 1) / pgn) * pgn);
+            const double cost = per_out / util * (bytes <= DW_SE_SMEM_TWO ? 1.0 : 1.6) * (1.0 + 0.02 * (6 - sh));   // fewer, larger groups on ties
+            if (cost < best_cost - 1e-9) { best_cost = cost; bx = x; by = y; bsh = sh; }
+        }
     }
-    if (best < 0) return false;
-    *cg_shift = best;
-    *smem = fixed + per_ch * ((size_t)1 << best);
+    if (bsh < 0) return false;
+    *xb = bx; *yb = by; *cg_shift = bsh;
+    *smem = fixed + per_ch * ((size_t)1 << bsh);
     return true;
 }
 
