@@ -35,6 +35,7 @@ constexpr int HALO_PIX = 3 * HALO_W;           // patch pixels: 3 input rows
 constexpr int MAX_HALO_SLOTS = 3;
 constexpr int MAX_EPI_WARPS = 16;    // one CTA per SM: 8 or 16 epilogue warps; two CTAs per SM: 4 each (warps 5.. of the CTA)
 constexpr int NTHREADS = (5 + MAX_EPI_WARPS) * 32;
+constexpr int NTHREADS_PW8 = (9 + MAX_EPI_WARPS) * 32;      // 8 producer warps (cp.async gather modes, one CTA per SM)
 static int g_epi_warps_one = 16;     // BN_EPI_WARPS=8|16 (development knob)
 
 __device__ __forceinline__ float act_fn(float v, int act) {
@@ -71,9 +72,15 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsi
 }
 
 // TWO: built for two co-resident CTAs per SM (288 threads, <= 113 registers) instead of one (up to 672 threads)
-template <int MODE, bool TWO = false>
-__global__ void __launch_bounds__(TWO ? 288 : NTHREADS, TWO ? 2 : 1)
+// PW: producer warps (4, or 8 for the cp.async gather modes: their per-chunk issue chain - table lookup, mask test,
+// 16 copies - is what bounds the deep-K and 3x3 layers, and it parallelises over rows).  Warp PW issues the MMAs,
+// warps PW+1.. are the epilogue.
+template <int MODE, bool TWO = false, int PW = 4>
+__global__ void __launch_bounds__(TWO ? 288 : (PW == 8 ? NTHREADS_PW8 : NTHREADS), TWO ? 2 : 1)
 k_tc_conv(const __grid_constant__ TcConvParams p) {
+    static_assert(PW == 4 || (PW == 8 && (MODE == TC_IN_PLANES || MODE == TC_IN_PLANES_SCALED || MODE == TC_IN_F32) && !TWO), "8 producer warps: gather modes only");
+    constexpr int RPT = 32 / PW;                // rows per producer thread
+    constexpr int RSTEP = 4 * PW;               // row distance between a thread's rows
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
@@ -89,7 +96,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NT = p.nt, STAGES = p.stages;
     const int nthreads = (int)blockDim.x;
-    const int epi_warps = (nthreads >> 5) - 5;
+    const int epi_warps = (nthreads >> 5) - (PW + 1);
     // narrow tiles (NT <= 32) with 8 epilogue warps: the per-tile epilogue is a latency chain, so the two
     // warp sets take alternate tiles (accumulator a <-> set a) instead of splitting the few columns
     const bool tile_split = epi_warps >= 8 && NT <= 32;
@@ -106,7 +113,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             // cp.async modes: 128 producer threads + thread 0's expect_tx arrive; TMA: thread 0 only
-            mbar_init(&bar_full[s], MODE == TC_IN_TMA ? 1 : (MODE == TC_IN_HALO ? 128 : 129));
+            mbar_init(&bar_full[s], MODE == TC_IN_TMA ? 1 : (MODE == TC_IN_HALO ? 128 : PW * 32 + 1));
             mbar_init(&bar_empty[s], 1);       // tcgen05.commit
         }
         mbar_init(&bar_w, 1);
@@ -116,7 +123,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(&tmem_holder, p.tmem_cols);
+    if (warp == PW) tmem_alloc(&tmem_holder, p.tmem_cols);
     // K unit -> (tap element offset, tap bit) table, shared by all tiles of this CTA
     for (int u = tid; u < p.k_chunks * 8; u += nthreads) {
         const int k0 = u * 8;
@@ -144,7 +151,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     // the epilogue staging tiles start after the ring
     const size_t ring_bytes = MODE == TC_IN_HALO ? (size_t)p.k_chunks * w_bytes + (size_t)STAGES * halo_slot_bytes
                                                  : (size_t)STAGES * stage_bytes;      // measured from `tiles`
-    if (MODE == TC_IN_HALO && warp < 4) {
+    if (MODE == TC_IN_HALO && warp < PW) {
         // ================================ halo-patch producers ================================
         const int n_tile = blockIdx.x % p.n_tiles;               // fixed per CTA (grid % n_tiles == 0)
         if (tid == 0) {
@@ -199,7 +206,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         }
         cp_async_wait_all();
         if (prof && tid == 0) { p.prof[0] = pw0; p.prof[1] = (unsigned long long)(clock64() - prof_t0); }
-    } else if (MODE == TC_IN_TMA && warp < 4) {
+    } else if (MODE == TC_IN_TMA && warp < PW) {
         // ================================ TMA producer (one thread) ================================
         if (tid == 0) {
             tma_prefetch_desc(&p.tmap);
@@ -253,31 +260,31 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             }
         }
         __syncwarp();
-    } else if (warp < 4) {
+    } else if (warp < PW) {
         // ================================ A / W producers ================================
-        // Per thread: one 16-byte K unit (8 channels) of 8 rows (rbase + 16*i).  Everything that
+        // Per thread: one 16-byte K unit (8 channels) of RPT rows (rbase + RSTEP*i).  Everything that
         // does not depend on the K chunk is hoisted to tile setup: per row a 32-bit element offset
         // of tap (0,0) and a bit mask of the taps that fall inside the image; per (chunk, unit) the
         // tap's element offset and bit index come from the smem table built above.
         const int unit = tid & 7;
         const int rbase = tid >> 3;
         const int hw = p.hout * p.wout;
-        const uint32_t dst0 = sw128_offset((uint32_t)rbase, (uint32_t)unit);   // row i: + i*2048
+        const uint32_t dst0 = sw128_offset((uint32_t)rbase, (uint32_t)unit);   // row i: + i * RSTEP * 128 (RSTEP is a multiple of 8 rows)
         const __half* in_lo = p.in_hi + p.in_plane;
         uint32_t s = 0, ph = 0;                // ring slot / phase of the chunk being issued
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int m0 = (t / p.n_tiles) * TM;
             const int n_tile = t - (t / p.n_tiles) * p.n_tiles;
-            int32_t pix_off[8];                // element offset of input pixel (iy0, ix0), channel 0
-            uint32_t tmask[8];                 // bit (ky*k + kx) set <=> tap inside the image
-            uint32_t seg_idx[8];
+            int32_t pix_off[RPT];              // element offset of input pixel (iy0, ix0), channel 0
+            uint32_t tmask[RPT];               // bit (ky*k + kx) set <=> tap inside the image
+            uint32_t seg_idx[RPT];
             {
                 int m = m0 + rbase;
                 int b = m / hw, rem = m - b * hw;
                 int oy = rem / p.wout, ox = rem - oy * p.wout;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (m + 16 * i < p.M) {
+                for (int i = 0; i < RPT; ++i) {
+                    if (m + RSTEP * i < p.M) {
                         const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
                         // taps kx in [xl, xh) and ky in [yl, yh) fall inside the image
                         const int xl = max(0, -ix0), xh = min(p.k, p.win - ix0);
@@ -293,7 +300,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                     } else {
                         tmask[i] = 0; pix_off[i] = 0; seg_idx[i] = 0;
                     }
-                    ox += 16;
+                    ox += RSTEP;
                     while (ox >= p.wout) { ox -= p.wout; ++oy; }
                     while (oy >= p.hout) { oy -= p.hout; ++b; }
                 }
@@ -313,21 +320,21 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 if (MODE == TC_IN_PLANES) {
                     const uint32_t d = smem_u32(st) + dst0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < RPT; ++i) {
                         const bool ok = (tmask[i] >> te.y) & 1u;
                         const int eo = ok ? pix_off[i] + te.x : 0;      // clamp: masked taps never form an address
                         const uint32_t nb = ok ? 16u : 0u;
-                        cp_async16(d + (uint32_t)i * 2048u, p.in_hi + eo, nb);
-                        cp_async16(d + (uint32_t)i * 2048u + A_TILE_BYTES, in_lo + eo, nb);
+                        cp_async16(d + (uint32_t)i * (RSTEP * 128u), p.in_hi + eo, nb);
+                        cp_async16(d + (uint32_t)i * (RSTEP * 128u) + A_TILE_BYTES, in_lo + eo, nb);
                     }
                     // the hardware arrives on the stage barrier once this thread's copies have landed:
                     // no wait in the producer, up to STAGES chunks in flight
                     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
                 } else {
-                    float vals[8][8];
+                    float vals[RPT][8];
                     const int ci = te.x - ((int)(te.y == 31 ? 0 : te.y) / p.k * p.win + (int)(te.y == 31 ? 0 : te.y) % p.k) * p.pix_stride;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < RPT; ++i) {
                         const bool ok = (tmask[i] >> te.y) & 1u;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) vals[i][e] = 0.f;
@@ -353,11 +360,11 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < RPT; ++i) {
                         uint4 hi, lo;
                         split8(vals[i], hi, lo);
-                        *reinterpret_cast<uint4*>(st + dst0 + i * 2048) = hi;
-                        *reinterpret_cast<uint4*>(st + dst0 + i * 2048 + A_TILE_BYTES) = lo;
+                        *reinterpret_cast<uint4*>(st + dst0 + i * (RSTEP * 128)) = hi;
+                        *reinterpret_cast<uint4*>(st + dst0 + i * (RSTEP * 128) + A_TILE_BYTES) = lo;
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&bar_full[s]);
@@ -367,7 +374,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         }
         if (MODE == TC_IN_PLANES) cp_async_wait_all();   // nothing may be in flight when the CTA exits
         if (prof && tid == 0) { p.prof[0] = pw0; p.prof[1] = (unsigned long long)(clock64() - prof_t0); }
-    } else if (warp == 4) {
+    } else if (warp == PW) {
         // ================================ MMA issuer ================================
         // Accumulator a = TMEM columns [a*2NT, a*2NT + 2NT): [main = A_hi*W_hi | corr = A_hi*W_lo + A_lo*W_hi].
         // The tensor core truncates when it adds into the FP32 accumulator; keeping the 2^-11-sized
@@ -471,7 +478,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         // staging tile [32 rows][32 columns] (16-byte chunks XOR-swizzled by row & 7).
         // Phase 2 (lanes along the channel axis): + residual, hi/lo split, 16-byte stores that cover
         // whole 32/64-byte row pieces (full sectors) instead of one 16-byte piece in each of 32 lines.
-        const int ew = warp - 5;
+        const int ew = warp - (PW + 1);
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         // tile_split: half of the warp sets serve accumulator 0, the other half accumulator 1
         const int nset_all = epi_warps >> 2;
@@ -490,7 +497,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const int lp = lp0 + lane;
             const uint32_t a = it & 1u;
             if (tile_split && (int)a != wset) continue;
-            mbar_wait_t(&bar_acc_full[a], (it >> 1) & 1u, pw0, prof && warp == 5);
+            mbar_wait_t(&bar_acc_full[a], (it >> 1) & 1u, pw0, prof && warp == PW + 1);
             tc_fence_after();
             const int row = sb * p.pix_per_seg + lp;
             const bool row_ok = lp < p.pix_per_seg && row < p.M;
@@ -672,11 +679,11 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             if (lane == 0) mbar_arrive(&bar_acc_empty[a]);
         }
         if (p.out_tma != 0 && lane == 0) bulk_wait_group0();     // shared memory must outlive the engine's reads
-        if (prof && warp == 5 && lane == 0) { p.prof[5] = pw0; p.prof[6] = (unsigned long long)(clock64() - prof_t0); }
+        if (prof && warp == PW + 1 && lane == 0) { p.prof[5] = pw0; p.prof[6] = (unsigned long long)(clock64() - prof_t0); }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == PW) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 constexpr size_t SMEM_TWO_PER_SM = 108 * 1024;     // dynamic bytes that still let two CTAs share an SM
@@ -732,6 +739,8 @@ cudaError_t tc_conv_init_device() {
     cudaError_t e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TWO_PER_SM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_tc_conv<TC_IN_PLANES_SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ONE_PER_SM);
     if (e != cudaSuccess) return e;
@@ -803,10 +812,13 @@ cudaError_t launch_tc_conv(const TcConvParams& pin, int num_sms, cudaStream_t st
         }
     }
     switch (p.in_mode) {
-        case TC_IN_PLANES:
+        case TC_IN_PLANES: {
+            static const bool pw8 = [] { const char* ev = getenv("BN_TC_PW"); return !(ev && atoi(ev) == 4); }();
             if (per_sm == 2) k_tc_conv<TC_IN_PLANES, true><<<grid, nthr, smem, stream>>>(p);
+            else if (pw8) k_tc_conv<TC_IN_PLANES, false, 8><<<grid, nthr + 128u, smem, stream>>>(p);
             else k_tc_conv<TC_IN_PLANES><<<grid, nthr, smem, stream>>>(p);
             break;
+        }
         case TC_IN_PLANES_SCALED: k_tc_conv<TC_IN_PLANES_SCALED><<<grid, nthr, smem, stream>>>(p); break;
         case TC_IN_TMA: k_tc_conv<TC_IN_TMA><<<grid, nthr, smem, stream>>>(p); break;
         default: k_tc_conv<TC_IN_F32><<<grid, nthr, smem, stream>>>(p); break;
