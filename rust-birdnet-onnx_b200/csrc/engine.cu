@@ -625,9 +625,13 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             tp.bias = d.bias;
             bool f32_rows = false;
             if (is_spatial(p, op.out) && op.kind == OP_CONV && (op.cout & 15) == 0) {
-                const int dwi = sole_dw_consumer(op.out);
-                DwSeParams sp;
-                f32_rows = dwi >= 0 && dw_se_plan((size_t)dwi, sp) >= 0 && sp.in_f32 != nullptr;
+                if (c->f32_out_cache.empty()) c->f32_out_cache.assign(p.ops.size(), -1);
+                if (c->f32_out_cache[i] < 0) {               // graph-only decision: made once per context
+                    const int dwi = sole_dw_consumer(op.out);
+                    DwSeParams sp;
+                    c->f32_out_cache[i] = (dwi >= 0 && dw_se_plan((size_t)dwi, sp) >= 0 && sp.in_f32 != nullptr) ? 1 : 0;
+                }
+                f32_rows = c->f32_out_cache[i] == 1;
             }
             if (f32_rows) {
                 tp.out_f32 = c->d_tensor[op.out];
@@ -959,7 +963,12 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
     const size_t seg_bytes = S * sizeof(float);
     // segments already in page-locked host memory: DMA straight from the caller's slices, contiguous runs as one copy
     {
-        bool all_pinned = true;
+        auto is_pinned = [](const void* ptr) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+            return at.type == cudaMemoryTypeHost;
+        };
+        bool all_pinned = is_pinned(seg_ptrs[0]);            // pageable callers pay for one query only
         for (uint64_t i = 0; i < B && all_pinned; ++i) {
             cudaPointerAttributes at{};
             const cudaError_t ce = cudaPointerGetAttributes(&at, seg_ptrs[i]);

@@ -95,6 +95,7 @@ struct bn_ctx {
     cudaEvent_t ev_results = nullptr;   // compute stream: logits / top-k of this run are final
     cudaEvent_t ev_fetched = nullptr;   // copy stream: the previous run's results have left the device buffers
     bool fetch_pending = false;
+    std::vector<int8_t> f32_out_cache;   // per plan op: -1 unknown, 0 planes output, 1 FP32 rows (hand-off to the fused depthwise kernel)
     float* h_in = nullptr;       // pinned [max_batch][S]
     float* d_in = nullptr;       // [max_batch][S]
     int16_t* h_pcm = nullptr;    // pinned [max_batch * S] 16-bit PCM staging (bn_ctx_run_pcm16), allocated on first use
