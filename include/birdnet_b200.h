@@ -197,6 +197,23 @@ int bn_pool_set_range_filter(bn_pool* pool, const uint8_t* state, const float* s
 int bn_pool_run(bn_pool* pool, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t n_segments,
                 const bn_run_opts* opts, float* logits, float* embeddings, bn_pred* topk, uint32_t* topk_count,
                 uint64_t topk_stride);
+/* Range-filter meta model.  Replaces the ONNX Runtime session RangeFilter owns:
+ * bn_meta_create   <- Session::builder()...commit_from_file + the "exactly one output" check (src/rangefilter.rs:239-258);
+ *                     the caller compares bn_meta_num_outputs with its label count (LabelCount, 260-266)
+ * bn_meta_predict  <- session.run on [1,3] = [latitude, longitude, week] + try_extract_tensor (src/rangefilter.rs:451-479);
+ *                     coordinate / date validation, calculate_week, thresholding and the sort stay in the host facade
+ * bn_meta_install_range_filter: the same forward pass, then the dense per-class tri-state of filter_predictions_impl
+ *                     (src/rangefilter.rs:333-386) built on the device and installed as the engine's fused range filter:
+ *                     species with score >= predict_threshold are "in the map" (predict returns only those, 482-496);
+ *                     in the map, score >= filter_threshold keeps (x score when rerank) and lower drops; the rest keep
+ *                     unchanged.  Requires the meta model's label list to be the classifier's (same order). */
+typedef struct bn_meta bn_meta;
+int bn_meta_create(const char* onnx_path, int32_t device_id, bn_meta** out);
+void bn_meta_destroy(bn_meta* meta);
+uint64_t bn_meta_num_outputs(const bn_meta* meta);
+int bn_meta_predict(bn_meta* meta, float latitude, float longitude, float week, float* scores, uint64_t n);
+int bn_meta_install_range_filter(bn_meta* meta, bn_engine* engine, float latitude, float longitude, float week,
+                                 float predict_threshold, float filter_threshold, int32_t rerank);
 int bn_device_count(void);
 /* Page-locked host memory for callers that want their segments DMA-able in place: when every segment pointer
  * handed to bn_ctx_run / bn_engine_run lies in page-locked host memory (from here, cudaHostAlloc or

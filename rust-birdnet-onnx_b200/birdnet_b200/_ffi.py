@@ -108,6 +108,11 @@ SIGNATURES = {
     "bn_pool_set_range_filter": (C.c_int, [_vp, _P(C.c_uint8), _P(C.c_float), C.c_uint64, C.c_int32]),
     "bn_pool_run": (C.c_int, [_vp, _P(_vp), _P(C.c_uint64), C.c_uint64, _P(RunOpts), _P(C.c_float),
                               _P(C.c_float), _P(Pred), _P(C.c_uint32), C.c_uint64]),
+    "bn_meta_create": (C.c_int, [C.c_char_p, C.c_int32, _P(_vp)]),
+    "bn_meta_destroy": (None, [_vp]),
+    "bn_meta_num_outputs": (C.c_uint64, [_vp]),
+    "bn_meta_predict": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, _P(C.c_float), C.c_uint64]),
+    "bn_meta_install_range_filter": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32]),
     "bn_device_count": (C.c_int, []),
     "bn_host_alloc": (C.c_void_p, [C.c_uint64]),
     "bn_host_free": (None, [C.c_void_p]),

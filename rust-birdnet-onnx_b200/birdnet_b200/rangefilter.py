@@ -149,15 +149,32 @@ class RangeFilterBuilder:                                   # rangefilter.rs:144
                     labels = parse_text_labels(f.read())
             except OSError as e:
                 raise LabelLoad(self._labels_path, str(e))
-        return RangeFilter(self._model_path, labels, self._threshold, self._device_id)
+        # load the meta model (rangefilter.rs:239-249), then the one-output and label-count checks (251-266)
+        handle = C.c_void_p()
+        raise_for_status(_ffi.lib.bn_meta_create(self._model_path.encode(), int(self._device_id), C.byref(handle)))
+        expected = int(_ffi.lib.bn_meta_num_outputs(handle))
+        if len(labels) != expected:
+            _ffi.lib.bn_meta_destroy(handle)
+            from .errors import LabelCount
+            raise LabelCount(expected, len(labels))
+        return RangeFilter(self._model_path, labels, self._threshold, self._device_id, handle)
 
 
 class RangeFilter:                                          # rangefilter.rs:389-579
-    def __init__(self, model_path: Optional[str], labels: List[str], threshold: float, device_id: int = 0):
+    def __init__(self, model_path: Optional[str], labels: List[str], threshold: float, device_id: int = 0, handle=None):
         self._model_path = model_path
         self._labels = labels
         self._threshold = threshold
         self._device_id = device_id
+        self._h = handle
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _ffi.lib.bn_meta_destroy(h)
+            except Exception:       # interpreter shutdown
+                pass
 
     @staticmethod
     def builder() -> RangeFilterBuilder:
@@ -174,9 +191,36 @@ class RangeFilter:                                          # rangefilter.rs:389
     def predict(self, latitude: float, longitude: float, month: int, day: int) -> List[LocationScore]:
         validate_coordinates(latitude, longitude)          # rangefilter.rs:443
         validate_date(month, day)                          # rangefilter.rs:446
-        raise RangeFilterInference(
-            "the meta-model MLP is SURVEY.md section 8f row 2 (next); supply location scores "
-            "to filter_predictions / Classifier.set_range_filter")
+        if not self._h:
+            raise RangeFilterInference("this RangeFilter was built without a meta model (from_labels)")
+        week = calculate_week(month, day)                  # rangefilter.rs:449
+        n = len(self._labels)
+        scores = np.empty(n, dtype=np.float32)
+        st = _ffi.lib.bn_meta_predict(self._h, float(latitude), float(longitude), week,
+                                      scores.ctypes.data_as(C.POINTER(C.c_float)), n)
+        if st != 0:
+            raise RangeFilterInference(_ffi.last_error())
+        thr = np.float32(self._threshold)
+        keep = np.nonzero(scores >= thr)[0]                # rangefilter.rs:482-496 (NaN >= thr is false, like Rust)
+        # sort_unstable_by(|a, b| b.score.total_cmp(&a.score)) (499); equal scores keep index order here
+        order = keep[np.argsort(-scores[keep], kind="stable")]
+        return [LocationScore(self._labels[i], float(scores[i]), int(i)) for i in order]
+
+    def install_on(self, classifier, latitude: float, longitude: float, month: int, day: int,
+                   filter_threshold: Optional[float] = None, rerank: bool = False) -> None:
+        """predict() + Classifier.set_range_filter() without leaving the device: the scores of this location are turned
+        into the dense per-class mask on the GPU and installed as the classifier's fused range filter (labels of both
+        must be the same list)."""
+        validate_coordinates(latitude, longitude)
+        validate_date(month, day)
+        if not self._h:
+            raise RangeFilterInference("this RangeFilter was built without a meta model (from_labels)")
+        if list(classifier.labels()) != list(self._labels):
+            raise RangeFilterInference("install_on needs identical label lists on the classifier and the range filter")
+        ft = self._threshold if filter_threshold is None else filter_threshold
+        raise_for_status(_ffi.lib.bn_meta_install_range_filter(
+            self._h, classifier._h, float(latitude), float(longitude), calculate_week(month, day),
+            float(self._threshold), float(ft), 1 if rerank else 0))
 
     def filter_predictions(self, predictions: Sequence[Prediction],
                            location_scores: Sequence[LocationScore], rerank: bool) -> List[Prediction]:
