@@ -8,6 +8,8 @@ with label strings — what classifier.rs:872-1058 does after `session.run`.
 from __future__ import annotations
 
 import ctypes as C
+import sys
+import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -36,20 +38,26 @@ def _run_opts(options: Optional[InferenceOptions]):
     return ro, options.timeout
 
 
+_addressof, _c_char = C.addressof, C.c_char
+
+
 def _segment_arrays(segments: Sequence) -> tuple:
     """Pointer + length arrays for B caller slices; slices stay where they are (no host pack
     here: the engine gathers them straight into pinned staging)."""
     n = len(segments)
-    keep = []
-    ptrs = (C.c_void_p * n)()
-    lens = (C.c_uint64 * n)()
-    for i, seg in enumerate(segments):
-        a = seg if (isinstance(seg, np.ndarray) and seg.dtype == np.float32 and seg.ndim == 1
-                    and seg.flags.c_contiguous) else np.ascontiguousarray(seg, dtype=np.float32).reshape(-1)
-        keep.append(a)
-        ptrs[i] = a.ctypes.data
-        lens[i] = a.shape[0]
-    return ptrs, lens, keep
+    f32 = np.dtype(np.float32)
+    keep = [seg if (type(seg) is np.ndarray and seg.dtype == f32 and seg.ndim == 1 and seg.flags.c_contiguous)
+            else np.ascontiguousarray(seg, dtype=np.float32).reshape(-1) for seg in segments]
+    # address / length tables as two numpy vectors (an order of magnitude cheaper than filling ctypes arrays item by item)
+    try:
+        fb = _c_char.from_buffer
+        addr = np.array([_addressof(fb(a)) for a in keep], dtype=np.uint64)
+    except (TypeError, ValueError):                          # read-only or empty slices: the slower attribute
+        addr = np.array([a.ctypes.data for a in keep], dtype=np.uint64)
+    size = np.array([a.shape[0] for a in keep], dtype=np.uint64)
+    keep.append(addr)
+    keep.append(size)
+    return addr.ctypes.data_as(C.POINTER(C.c_void_p)), size.ctypes.data_as(C.POINTER(C.c_uint64)), keep
 
 
 class ClassifierBuilder:
@@ -267,6 +275,8 @@ class Classifier:
 
     def __init__(self, handle, config, labels, requested, top_k, min_confidence, info):
         self._h = handle
+        self._pool: List[np.ndarray] = []
+        self._pool_lock = threading.Lock()
         self._config = config
         self._labels = labels
         self._requested = requested
@@ -386,12 +396,36 @@ class Classifier:
         raise_for_status(st, timeout)
         return self._results(out)
 
+    _BLOCK_POOL_MAX = 16
+
+    def _owned_block(self, rows: int, cols: int) -> np.ndarray:
+        """[rows, cols] f32 block the results of one call own (their raw_scores / embeddings rows are views of it).
+        Blocks whose results the caller has dropped are handed out again, so a steady stream of calls touches no fresh
+        pages: a block is free exactly when nothing but the pool references it (every view of it, however derived,
+        holds a reference to it through `.base`)."""
+        shape = (rows, cols)
+        with self._pool_lock:
+            for blk in self._pool:
+                if blk.shape == shape and sys.getrefcount(blk) == 3:     # the pool's list, `blk`, getrefcount's argument
+                    return blk.view()
+            blk = np.empty(shape, dtype=np.float32)
+            if len(self._pool) >= self._BLOCK_POOL_MAX:
+                self._pool.pop(0)
+            self._pool.append(blk)
+            return blk.view()
+
     def _results(self, out) -> List[PredictionResult]:
         """process_batch_outputs_from_flat (classifier.rs:872-911) on the borrowed slabs."""
         B, N, E, K = int(out.batch), int(out.num_species), int(out.embedding_dim), int(out.topk_stride)
         mt = self._config.model_type
-        logits = np.ctypeslib.as_array(out.logits, shape=(B, N)).copy()
-        emb = np.ctypeslib.as_array(out.embeddings, shape=(B, E)).copy() if (E and out.embeddings) else None
+        # the copies out of the borrowed slabs (raw_scores / embeddings are owned Vec<f32> in the reference) go through
+        # memmove: a foreign call, so other driver threads run while the 6.7 MB move
+        logits = self._owned_block(B, N)
+        C.memmove(logits.ctypes.data, out.logits, logits.nbytes)
+        emb = None
+        if E and out.embeddings:
+            emb = self._owned_block(B, E)
+            C.memmove(emb.ctypes.data, out.embeddings, emb.nbytes)
         counts = np.ctypeslib.as_array(out.topk_count, shape=(B,)).tolist()
         labels = self._labels
         nl = len(labels)

@@ -301,6 +301,8 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
         BN_CUDA(up(off.data(), off.size() * sizeof(int), (void**)&lm.mel_off));
         BN_CUDA(up(wv.data(), wv.size() * sizeof(float), (void**)&lm.mel_w));
     }
+    BN_CUDA(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+    BN_CUDA(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     *out = e.release();
     return BN_OK;
 }
@@ -323,12 +325,16 @@ bn_engine::~bn_engine() {
     if (fe_lm.mel_cnt) cudaFree(fe_lm.mel_cnt);
     if (fe_lm.mel_off) cudaFree(fe_lm.mel_off);
     if (fe_lm.mel_w) cudaFree(fe_lm.mel_w);
+    if (compute) cudaStreamDestroy(compute);
+    if (h2d) cudaStreamDestroy(h2d);
 }
 
 bn_ctx::~bn_ctx() {
     if (!eng) return;
     cudaSetDevice(eng->device);
     if (stream) cudaStreamSynchronize(stream);
+    if (in_stream && in_stream != stream) cudaStreamSynchronize(in_stream);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
     if (h_in) cudaFreeHost(h_in);
     if (h_pcm) cudaFreeHost(h_pcm);
     if (d_pcm) cudaFree(d_pcm);
@@ -346,8 +352,10 @@ bn_ctx::~bn_ctx() {
     if (h_count) cudaFreeHost(h_count);
     for (auto ev : prof_events) cudaEventDestroy(ev);
     if (done) cudaEventDestroy(done);
-    if (stream) cudaStreamDestroy(stream);
+    if (in_stream && in_stream != stream) cudaStreamDestroy(in_stream);
+    if (stream && owns_stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_in) cudaEventDestroy(ev_in);
     if (ev_results) cudaEventDestroy(ev_results);
     if (ev_fetched) cudaEventDestroy(ev_fetched);
 }
@@ -364,8 +372,17 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     const Plan& p = e->plan;
     const size_t S = (size_t)p.sample_count;
     const size_t mb = std::max<uint64_t>(max_batch, 1);
-    BN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    static const bool shared_lane = [] { const char* ev = getenv("BN_SHARED_COMPUTE"); return !(ev && ev[0] == '0'); }();
+    if (shared_lane && e->compute) {
+        c->stream = e->compute;
+        c->owns_stream = false;
+        BN_CUDA(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+    } else {
+        BN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->in_stream = c->stream;
+    }
     BN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    BN_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     BN_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
     BN_CUDA(cudaEventCreateWithFlags(&c->ev_results, cudaEventDisableTiming));
     BN_CUDA(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
@@ -894,6 +911,8 @@ static int begin_run(bn_ctx* c, PostCfg& post, uint64_t& k_eff, const bn_run_opt
     bn_engine* e = c->eng;
     BN_CUDA(cudaSetDevice(e->device));
     if (c->draining) {                       // a timed-out / cancelled run may still be in flight
+        BN_CUDA(cudaStreamSynchronize(c->in_stream));
+        if (!c->owns_stream) BN_CUDA(cudaStreamSynchronize(e->h2d));
         BN_CUDA(cudaStreamSynchronize(c->stream));
         BN_CUDA(cudaStreamSynchronize(c->copy_stream));
         c->draining = false;
@@ -923,12 +942,16 @@ int ctx_enqueue_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fet
     uint64_t k_eff = 0;
     int st = begin_run(c, post, k_eff, opts);
     if (st != BN_OK) return st;
-    st = enqueue_forward(c, d_audio, (int)batch, post, k_eff);
-    if (st != BN_OK) return st;
-    if (fetch) { st = enqueue_fetch(c, (int)batch, k_eff); if (st != BN_OK) return st; }
-    prof_mark(c, "end");
-    st = record_done(c, fetch);
-    if (st != BN_OK) return st;
+    {
+        std::unique_lock<std::mutex> lane(c->eng->launch_mu, std::defer_lock);
+        if (!c->owns_stream) lane.lock();                  // a whole batch enters the shared lane at a time
+        st = enqueue_forward(c, d_audio, (int)batch, post, k_eff);
+        if (st != BN_OK) return st;
+        if (fetch) { st = enqueue_fetch(c, (int)batch, k_eff); if (st != BN_OK) return st; }
+        prof_mark(c, "end");
+        st = record_done(c, fetch);
+        if (st != BN_OK) return st;
+    }
     c->pending_batch = batch;
     c->pending_k = k_eff;
     return BN_OK;
@@ -957,39 +980,38 @@ int ctx_run_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fetch, 
 }
 
 // ---- host staging: gather caller slices into the pinned slab and ship them chunk by chunk ----
+// every slice (first and last byte) lies in page-locked host memory: the DMA engine can read it where it is
+static bool segments_page_locked(const float* const* seg_ptrs, uint64_t B, size_t seg_bytes) {
+    auto is_pinned = [](const void* ptr) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    if (!is_pinned(seg_ptrs[0])) return false;               // pageable callers pay for one query only
+    for (uint64_t i = 0; i < B; ++i)                          // a slice may straddle the end of a registered range
+        if (!is_pinned(seg_ptrs[i]) || !is_pinned(reinterpret_cast<const char*>(seg_ptrs[i]) + seg_bytes - 1)) return false;
+    return true;
+}
+
+// DMA straight from the caller's page-locked slices, contiguous runs as one copy
+static int copy_page_locked_segments(bn_ctx* c, const float* const* seg_ptrs, uint64_t B, cudaStream_t s) {
+    const size_t S = (size_t)c->eng->plan.sample_count;
+    const size_t seg_bytes = S * sizeof(float);
+    uint64_t i = 0;
+    while (i < B) {
+        uint64_t j = i + 1;
+        while (j < B && seg_ptrs[j] == seg_ptrs[j - 1] + S && (j - i) < 32) ++j;     // <= 32 segments (18 MB) per copy
+        BN_CUDA(cudaMemcpyAsync(c->d_in + i * S, seg_ptrs[i], (j - i) * seg_bytes, cudaMemcpyHostToDevice, s));
+        i = j;
+    }
+    return BN_OK;
+}
+
+// pageable slices: gather into the pinned slab and ship chunk by chunk on this context's input stream
 static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
     bn_engine* e = c->eng;
     const size_t S = (size_t)e->plan.sample_count;
     const size_t seg_bytes = S * sizeof(float);
-    // segments already in page-locked host memory: DMA straight from the caller's slices, contiguous runs as one copy
-    {
-        auto is_pinned = [](const void* ptr) {
-            cudaPointerAttributes at{};
-            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
-            return at.type == cudaMemoryTypeHost;
-        };
-        bool all_pinned = is_pinned(seg_ptrs[0]);            // pageable callers pay for one query only
-        for (uint64_t i = 0; i < B && all_pinned; ++i) {
-            cudaPointerAttributes at{};
-            const cudaError_t ce = cudaPointerGetAttributes(&at, seg_ptrs[i]);
-            if (ce != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
-            // the last byte must be page-locked too (a slice may straddle the end of a registered range)
-            cudaPointerAttributes at2{};
-            const cudaError_t ce2 = cudaPointerGetAttributes(&at2, reinterpret_cast<const char*>(seg_ptrs[i]) + seg_bytes - 1);
-            if (ce2 != cudaSuccess) { cudaGetLastError(); all_pinned = false; break; }
-            all_pinned = at.type == cudaMemoryTypeHost && at2.type == cudaMemoryTypeHost;
-        }
-        if (all_pinned) {
-            uint64_t i = 0;
-            while (i < B) {
-                uint64_t j = i + 1;
-                while (j < B && seg_ptrs[j] == seg_ptrs[j - 1] + S && (j - i) < 32) ++j;     // <= 32 segments (18 MB) per copy: the kernels can start early
-                BN_CUDA(cudaMemcpyAsync(c->d_in + i * S, seg_ptrs[i], (j - i) * seg_bytes, cudaMemcpyHostToDevice, c->stream));
-                i = j;
-            }
-            return BN_OK;
-        }
-    }
     const uint64_t chunk = 8;
     const uint64_t n_chunks = (B + chunk - 1) / chunk;
     int T = (int)std::min<uint64_t>((uint64_t)e->pack_threads, n_chunks);
@@ -997,7 +1019,7 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
         for (uint64_t ci = 0; ci < n_chunks; ++ci) {
             uint64_t lo = ci * chunk, hi = std::min(B, lo + chunk);
             for (uint64_t i = lo; i < hi; ++i) stream_copy(c->h_in + i * S, seg_ptrs[i], seg_bytes);   // batch_context.rs:209-211
-            BN_CUDA(cudaMemcpyAsync(c->d_in + lo * S, c->h_in + lo * S, (hi - lo) * seg_bytes, cudaMemcpyHostToDevice, c->stream));
+            BN_CUDA(cudaMemcpyAsync(c->d_in + lo * S, c->h_in + lo * S, (hi - lo) * seg_bytes, cudaMemcpyHostToDevice, c->in_stream));
         }
         return BN_OK;
     }
@@ -1010,7 +1032,7 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
             if (ci >= n_chunks) break;
             uint64_t lo = ci * chunk, hi = std::min(B, lo + chunk);
             for (uint64_t i = lo; i < hi; ++i) stream_copy(c->h_in + i * S, seg_ptrs[i], seg_bytes);
-            cudaError_t ce = cudaMemcpyAsync(c->d_in + lo * S, c->h_in + lo * S, (hi - lo) * seg_bytes, cudaMemcpyHostToDevice, c->stream);
+            cudaError_t ce = cudaMemcpyAsync(c->d_in + lo * S, c->h_in + lo * S, (hi - lo) * seg_bytes, cudaMemcpyHostToDevice, c->in_stream);
             if (ce != cudaSuccess) err.store((int)ce);
         }
     };
@@ -1022,6 +1044,20 @@ static int stage_input(bn_ctx* c, const float* const* seg_ptrs, uint64_t B) {
     if (err.load() != (int)cudaSuccess) return cuda_fail((cudaError_t)err.load(), "cudaMemcpyAsync(H2D)");
     return BN_OK;
 }
+
+// BN_TRACE_RUN=1 (dev aid): one stderr line per bn_ctx_run with host timestamps and device timestamps of the H2D copy,
+// the forward pass and the fetch, all in ms since the first traced call
+struct RunTrace {
+    cudaEvent_t ref = nullptr;
+    std::chrono::steady_clock::time_point host0;
+    std::mutex mu;
+};
+static RunTrace g_trace;
+static bool trace_enabled() {
+    static const bool v = [] { const char* ev = getenv("BN_TRACE_RUN"); return ev && ev[0] == '1'; }();
+    return v;
+}
+static double host_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_trace.host0).count(); }
 
 int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
                  bool check_max_first, const bn_run_opts* opts, bn_outputs* out) {
@@ -1040,18 +1076,69 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
     uint64_t k_eff = 0;
     int st = begin_run(c, post, k_eff, opts);
     if (st != BN_OK) return st;
-    prof_mark(c, "h2d");
-    st = stage_input(c, seg_ptrs, batch);
-    if (st != BN_OK) return st;
-    st = enqueue_forward(c, c->d_in, (int)batch, post, k_eff);
-    if (st != BN_OK) return st;
-    st = enqueue_fetch(c, (int)batch, k_eff);
-    if (st != BN_OK) return st;
-    prof_mark(c, "end");
-    st = record_done(c, true);
-    if (st != BN_OK) return st;
+    const bool tr = trace_enabled() && !c->owns_stream;
+    cudaEvent_t te[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double th[5] = {0, 0, 0, 0, 0};
+    if (tr) {
+        std::lock_guard<std::mutex> lk(g_trace.mu);
+        if (!g_trace.ref) {
+            cudaEventCreate(&g_trace.ref);
+            cudaDeviceSynchronize();
+            cudaEventRecord(g_trace.ref, c->eng->h2d);
+            cudaEventSynchronize(g_trace.ref);
+            g_trace.host0 = std::chrono::steady_clock::now();
+        }
+        for (auto& e : te) cudaEventCreate(&e);
+        th[0] = host_ms();
+    }
+    const bool in_place = segments_page_locked(seg_ptrs, batch, (size_t)S * sizeof(float));
+    if (tr) th[1] = host_ms();
+    if (c->owns_stream) prof_mark(c, "h2d");
+    if (!in_place || c->owns_stream) {
+        st = in_place ? copy_page_locked_segments(c, seg_ptrs, batch, c->in_stream) : stage_input(c, seg_ptrs, batch);
+        if (st != BN_OK) return st;
+    }
+    {
+        std::unique_lock<std::mutex> lane(c->eng->launch_mu, std::defer_lock);
+        if (!c->owns_stream) {                             // a whole batch enters the shared lanes at a time
+            cudaStream_t src = c->in_stream;
+            if (in_place) {
+                // page-locked input goes through the engine's one H2D lane: copies of concurrent callers run one after
+                // the other in the order their kernels will, instead of sharing PCIe and all arriving late
+                lane.lock();
+                if (tr) { th[2] = host_ms(); cudaEventRecord(te[0], c->eng->h2d); }
+                st = copy_page_locked_segments(c, seg_ptrs, batch, c->eng->h2d);
+                if (st != BN_OK) return st;
+                src = c->eng->h2d;
+                if (tr) cudaEventRecord(te[1], c->eng->h2d);
+            }
+            BN_CUDA(cudaEventRecord(c->ev_in, src));
+            if (!in_place) lane.lock();
+            prof_mark(c, "h2d");                           // on the lane: the time the lane waits for this batch's input
+            BN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+            if (tr) cudaEventRecord(te[2], c->stream);
+        }
+        st = enqueue_forward(c, c->d_in, (int)batch, post, k_eff);
+        if (st != BN_OK) return st;
+        if (tr) cudaEventRecord(te[3], c->stream);
+        st = enqueue_fetch(c, (int)batch, k_eff);
+        if (st != BN_OK) return st;
+        prof_mark(c, "end");
+        st = record_done(c, true);
+        if (st != BN_OK) return st;
+        if (tr) { cudaEventRecord(te[4], c->copy_stream); th[3] = host_ms(); }
+    }
     st = wait_done(c, opts);
     if (st != BN_OK) return st;
+    if (tr) {
+        th[4] = host_ms();
+        float g[5] = {0, 0, 0, 0, 0};
+        cudaEventSynchronize(te[4]);
+        for (int i = 0; i < 5; ++i) if (in_place || i >= 2) cudaEventElapsedTime(&g[i], g_trace.ref, te[i]);
+        fprintf(stderr, "[trace] ctx=%p host: enter %.2f checked %.2f locked %.2f enqueued %.2f done %.2f | gpu: h2d %.2f-%.2f fwd %.2f-%.2f fetched %.2f\n",
+                (void*)c, th[0], th[1], th[2], th[3], th[4], g[0], g[1], g[2], g[3], g[4]);
+        for (auto& e : te) cudaEventDestroy(e);
+    }
     fill_outputs(c, batch, k_eff, out);
     if (c->profiling) {
         size_t n = c->prof_names.size();
@@ -1099,17 +1186,34 @@ int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t fi
         const size_t m = std::min(piece, n - o);
         const int16_t* src = pcm + first_pos + o;
         if (!pinned) { stream_copy(c->h_pcm + o, src, m * sizeof(int16_t)); src = c->h_pcm + o; }
-        BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, src, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+        if (pinned && !c->owns_stream) continue;                    // goes through the engine's H2D lane below
+        BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, src, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->in_stream));
     }
-    BN_CUDA(launch_pcm16_to_segments(c->d_pcm, first_pos, n_samples, first_pos, step, c->d_in, (int)batch, (int)S, c->stream));
-    st = enqueue_forward(c, c->d_in, (int)batch, post, k_eff);
-    if (st != BN_OK) return st;
-    c->last_launches += 1;
-    st = enqueue_fetch(c, (int)batch, k_eff);
-    if (st != BN_OK) return st;
-    prof_mark(c, "end");
-    st = record_done(c, true);
-    if (st != BN_OK) return st;
+    {
+        std::unique_lock<std::mutex> lane(c->eng->launch_mu, std::defer_lock);
+        if (!c->owns_stream) {
+            cudaStream_t src_stream = c->in_stream;
+            if (pinned) {
+                lane.lock();
+                for (size_t o = 0; o < n; o += piece)
+                    BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, pcm + first_pos + o, std::min(piece, n - o) * sizeof(int16_t),
+                                            cudaMemcpyHostToDevice, c->eng->h2d));
+                src_stream = c->eng->h2d;
+            }
+            BN_CUDA(cudaEventRecord(c->ev_in, src_stream));
+            if (!pinned) lane.lock();
+            BN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+        }
+        BN_CUDA(launch_pcm16_to_segments(c->d_pcm, first_pos, n_samples, first_pos, step, c->d_in, (int)batch, (int)S, c->stream));
+        st = enqueue_forward(c, c->d_in, (int)batch, post, k_eff);
+        if (st != BN_OK) return st;
+        c->last_launches += 1;
+        st = enqueue_fetch(c, (int)batch, k_eff);
+        if (st != BN_OK) return st;
+        prof_mark(c, "end");
+        st = record_done(c, true);
+        if (st != BN_OK) return st;
+    }
     st = wait_done(c, opts);
     if (st != BN_OK) return st;
     fill_outputs(c, batch, k_eff, out);

@@ -83,14 +83,23 @@ struct bn_engine {
     bn::PostCfg post;
     std::mutex ctx_mu;
     std::map<std::thread::id, bn_ctx*> thread_ctx;   // bn_engine_run: one context per calling thread
+    // One compute lane per engine: every context's kernels go to this stream, one whole batch at a time (launch_mu), so
+    // batches of concurrent callers run back to back instead of time-slicing the SMs; their H2D / D2H copies stay on
+    // per-context streams and overlap the lane.  BN_SHARED_COMPUTE=0 gives every context a private compute stream.
+    cudaStream_t compute = nullptr;
+    cudaStream_t h2d = nullptr;     // page-locked caller memory is copied on this one lane, in kernel order
+    std::mutex launch_mu;
     ~bn_engine();
 };
 
 struct bn_ctx {
     bn_engine* eng = nullptr;
     uint64_t max_batch = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // compute: the engine's lane (shared) or a private stream
+    bool owns_stream = true;
+    cudaStream_t in_stream = nullptr;   // H2D staging of this context (== stream when the compute stream is private)
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_in = nullptr;        // in_stream: this run's input is on the device
     cudaEvent_t done = nullptr;
     cudaEvent_t ev_results = nullptr;   // compute stream: logits / top-k of this run are final
     cudaEvent_t ev_fetched = nullptr;   // copy stream: the previous run's results have left the device buffers

@@ -203,3 +203,25 @@ def test_dense_range_state_is_string_keyed():
     state, score = dense_range_state(labels, loc, 0.03)
     assert state.tolist() == [1, 2, 0, 1]
     assert np.allclose(score, [0.5, 0.02, 0.0, 0.5])      # last duplicate wins, like HashMap::collect
+
+
+def test_result_blocks_are_reused_only_when_unreferenced():
+    """raw_scores / embeddings rows are views of a per-call block (classifier.rs:897-903 hands out owned Vecs); a block
+    goes back into circulation only when the caller has dropped every view of it."""
+    import threading
+    from birdnet_b200.classifier import Classifier
+    c = Classifier.__new__(Classifier)
+    c._pool, c._pool_lock = [], threading.Lock()
+    addr = lambda a: a.__array_interface__["data"][0]
+    a = c._owned_block(4, 10)
+    first, row = addr(a), a[2]
+    b = c._owned_block(4, 10)
+    assert addr(b) != first                       # a is alive
+    del a
+    assert addr(c._owned_block(4, 10)) != first   # a row of it is alive
+    del row
+    assert addr(c._owned_block(4, 10)) == first   # nothing refers to it any more
+    assert addr(c._owned_block(5, 10)) != first   # other shapes get their own
+    for _ in range(40):                           # bounded
+        keep = [c._owned_block(2, 2) for _ in range(3)]
+    assert len(c._pool) <= Classifier._BLOCK_POOL_MAX
