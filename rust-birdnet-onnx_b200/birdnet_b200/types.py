@@ -45,14 +45,14 @@ class ModelConfig:                       # types.rs:72-85
     embedding_dim: Optional[int]
 
 
-@dataclass
+@dataclass(slots=True)
 class Prediction:                        # types.rs:89-96
     species: str
     confidence: float
     index: int
 
 
-@dataclass
+@dataclass(slots=True)
 class PredictionResult:                  # types.rs:100-109
     model_type: ModelType
     predictions: List[Prediction]
@@ -60,7 +60,7 @@ class PredictionResult:                  # types.rs:100-109
     raw_scores: np.ndarray
 
 
-@dataclass
+@dataclass(slots=True)
 class LocationScore:                     # types.rs:113-120
     species: str
     score: float
