@@ -83,6 +83,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {   
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync).  Issue tcgen05.mma under this predicate rather than `lane == 0`: ptxas
+// recognises the single-lane region and feeds the uniform-register operands with plain R2UR instead of an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop per operand (measured: 64.7 -> 39 cycles per small-N MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16/bf16 inputs, fp32 accumulate), one thread issues
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

@@ -395,7 +395,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 halo_db[i] = umma_desc_sw128(smem_u32(tiles) + (uint32_t)(k >> 6) * w_bytes) + (uint64_t)(kDescKStep * ((k & 63) >> 4));
             }
             __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {     // elect.sync: ptxas then knows a single lane runs the loop and moves descriptors with plain R2UR
             const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint64_t lo_delta = (uint64_t)(halo_plane_bytes >> 4);
             mbar_wait(&bar_w, 0);
@@ -421,7 +421,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             }
             if (prof) { p.prof[2] = pw0; p.prof[3] = pw1; p.prof[4] = (unsigned long long)(clock64() - prof_t0); p.prof[7] = it; }
           }
-        } else if (MODE != TC_IN_HALO && lane == 0) {
+        } else if (MODE != TC_IN_HALO && elect_one()) {
             const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
             if (w_res) mbar_wait(&bar_w, 0);
