@@ -174,6 +174,9 @@ uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx);
 int bn_ctx_set_profiling(bn_ctx* ctx, int32_t enabled);
 int bn_ctx_stage_times(const bn_ctx* ctx, float* ms_out, char (*names_out)[48], uint64_t cap, uint64_t* n_out);
 void* bn_ctx_stream(bn_ctx* ctx);                      /* cudaStream_t the kernels run on */
+/* Compute lanes of the engine: contexts are assigned to them in turn at creation; batches of contexts on the same
+ * lane run back to back, batches on different lanes overlap (BN_COMPUTE_LANES=1|2, default 2). */
+int32_t bn_engine_compute_lanes(const bn_engine* engine);
 
 /* RangeFilter::filter_predictions / filter_batch_predictions on lists already selected
  * (src/rangefilter.rs:527-579), executed on the engine's device. */

@@ -96,6 +96,7 @@ SIGNATURES = {
     "bn_ctx_set_profiling": (C.c_int, [_vp, C.c_int32]),
     "bn_ctx_stage_times": (C.c_int, [_vp, _P(C.c_float), _vp, C.c_uint64, _P(C.c_uint64)]),
     "bn_ctx_stream": (_vp, [_vp]),
+    "bn_engine_compute_lanes": (C.c_int32, [_vp]),
     "bn_range_filter_apply": (C.c_int, [_vp, _P(Pred), _P(C.c_uint32), C.c_uint64, C.c_uint64,
                                         _P(C.c_uint8), _P(C.c_float), C.c_uint64, C.c_int32,
                                         _P(Pred), _P(C.c_uint32)]),

@@ -316,6 +316,10 @@ class Classifier:
             self._h, state.ctypes.data_as(C.POINTER(C.c_uint8)),
             score.ctypes.data_as(C.POINTER(C.c_float)), len(state), 1 if rerank else 0))
 
+    def compute_lanes(self) -> int:
+        """Number of compute lanes of the engine (contexts are assigned to them in turn)."""
+        return int(_lib.bn_engine_compute_lanes(self._h))
+
     def clear_range_filter(self) -> None:
         raise_for_status(_lib.bn_engine_clear_range_filter(self._h))
 

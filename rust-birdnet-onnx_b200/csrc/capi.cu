@@ -248,6 +248,7 @@ int bn_ctx_stage_times(const bn_ctx* ctx, float* ms_out, char (*names_out)[48], 
     return BN_OK;
 }
 void* bn_ctx_stream(bn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int32_t bn_engine_compute_lanes(const bn_engine* engine) { return engine ? engine->n_lanes : 0; }
 
 int bn_range_filter_apply(bn_engine* engine, const bn_pred* in, const uint32_t* in_count, uint64_t rows,
                           uint64_t stride, const uint8_t* state, const float* score, uint64_t n, int32_t rerank,

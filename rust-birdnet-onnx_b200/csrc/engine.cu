@@ -301,7 +301,8 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
         BN_CUDA(up(off.data(), off.size() * sizeof(int), (void**)&lm.mel_off));
         BN_CUDA(up(wv.data(), wv.size() * sizeof(float), (void**)&lm.mel_w));
     }
-    BN_CUDA(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+    { const char* ev = getenv("BN_COMPUTE_LANES"); if (ev && atoi(ev) >= 1 && atoi(ev) <= bn_engine::MAX_LANES) e->n_lanes = atoi(ev); }
+    for (int l = 0; l < e->n_lanes; ++l) BN_CUDA(cudaStreamCreateWithFlags(&e->compute[l], cudaStreamNonBlocking));
     BN_CUDA(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     *out = e.release();
     return BN_OK;
@@ -325,7 +326,7 @@ bn_engine::~bn_engine() {
     if (fe_lm.mel_cnt) cudaFree(fe_lm.mel_cnt);
     if (fe_lm.mel_off) cudaFree(fe_lm.mel_off);
     if (fe_lm.mel_w) cudaFree(fe_lm.mel_w);
-    if (compute) cudaStreamDestroy(compute);
+    for (auto& l : compute) if (l) cudaStreamDestroy(l);
     if (h2d) cudaStreamDestroy(h2d);
 }
 
@@ -373,8 +374,9 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     const size_t S = (size_t)p.sample_count;
     const size_t mb = std::max<uint64_t>(max_batch, 1);
     static const bool shared_lane = [] { const char* ev = getenv("BN_SHARED_COMPUTE"); return !(ev && ev[0] == '0'); }();
-    if (shared_lane && e->compute) {
-        c->stream = e->compute;
+    if (shared_lane && e->compute[0]) {
+        c->lane = e->next_lane.fetch_add(1) % e->n_lanes;
+        c->stream = e->compute[c->lane];
         c->owns_stream = false;
         BN_CUDA(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
     } else {
@@ -943,7 +945,7 @@ int ctx_enqueue_device(bn_ctx* c, const float* d_audio, uint64_t batch, bool fet
     int st = begin_run(c, post, k_eff, opts);
     if (st != BN_OK) return st;
     {
-        std::unique_lock<std::mutex> lane(c->eng->launch_mu, std::defer_lock);
+        std::unique_lock<std::mutex> lane(c->eng->launch_mu[c->lane], std::defer_lock);
         if (!c->owns_stream) lane.lock();                  // a whole batch enters the shared lane at a time
         st = enqueue_forward(c, d_audio, (int)batch, post, k_eff);
         if (st != BN_OK) return st;
@@ -1099,20 +1101,21 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
         if (st != BN_OK) return st;
     }
     {
-        std::unique_lock<std::mutex> lane(c->eng->launch_mu, std::defer_lock);
+        std::unique_lock<std::mutex> lane(c->eng->launch_mu[c->lane], std::defer_lock);
         if (!c->owns_stream) {                             // a whole batch enters the shared lanes at a time
             cudaStream_t src = c->in_stream;
             if (in_place) {
                 // page-locked input goes through the engine's one H2D lane: copies of concurrent callers run one after
                 // the other in the order their kernels will, instead of sharing PCIe and all arriving late
                 lane.lock();
+                std::lock_guard<std::mutex> hl(c->eng->h2d_mu);     // always lane -> h2d
                 if (tr) { th[2] = host_ms(); cudaEventRecord(te[0], c->eng->h2d); }
                 st = copy_page_locked_segments(c, seg_ptrs, batch, c->eng->h2d);
                 if (st != BN_OK) return st;
-                src = c->eng->h2d;
                 if (tr) cudaEventRecord(te[1], c->eng->h2d);
-            }
-            BN_CUDA(cudaEventRecord(c->ev_in, src));
+                BN_CUDA(cudaEventRecord(c->ev_in, c->eng->h2d));
+            } else
+                BN_CUDA(cudaEventRecord(c->ev_in, src));
             if (!in_place) lane.lock();
             prof_mark(c, "h2d");                           // on the lane: the time the lane waits for this batch's input
             BN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
@@ -1190,17 +1193,18 @@ int ctx_run_pcm16(bn_ctx* c, const int16_t* pcm, uint64_t n_samples, uint64_t fi
         BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, src, m * sizeof(int16_t), cudaMemcpyHostToDevice, c->in_stream));
     }
     {
-        std::unique_lock<std::mutex> lane(c->eng->launch_mu, std::defer_lock);
+        std::unique_lock<std::mutex> lane(c->eng->launch_mu[c->lane], std::defer_lock);
         if (!c->owns_stream) {
             cudaStream_t src_stream = c->in_stream;
             if (pinned) {
                 lane.lock();
+                std::lock_guard<std::mutex> hl(c->eng->h2d_mu);     // always lane -> h2d
                 for (size_t o = 0; o < n; o += piece)
                     BN_CUDA(cudaMemcpyAsync(c->d_pcm + o, pcm + first_pos + o, std::min(piece, n - o) * sizeof(int16_t),
                                             cudaMemcpyHostToDevice, c->eng->h2d));
-                src_stream = c->eng->h2d;
-            }
-            BN_CUDA(cudaEventRecord(c->ev_in, src_stream));
+                BN_CUDA(cudaEventRecord(c->ev_in, c->eng->h2d));
+            } else
+                BN_CUDA(cudaEventRecord(c->ev_in, src_stream));
             if (!pinned) lane.lock();
             BN_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
         }

@@ -208,7 +208,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         if (prof && tid == 0) { p.prof[0] = pw0; p.prof[1] = (unsigned long long)(clock64() - prof_t0); }
     } else if (MODE == TC_IN_TMA && warp < PW) {
         // ================================ TMA producer (one thread) ================================
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tma_prefetch_desc(&p.tmap);
             if (w_res) {
                 const int n_res = blockIdx.x % p.n_tiles;                 // fixed per CTA (grid % n_tiles == 0)
@@ -308,7 +308,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             for (int kc = 0; kc < p.k_chunks; ++kc) {
                 mbar_wait_t(&bar_empty[s], ph ^ 1u, pw0, prof);
                 uint8_t* st = tiles + (size_t)s * stage_bytes;
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {
                     asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
                                  ::"r"(smem_u32(&bar_full[s])), "r"(w_bytes) : "memory");
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
@@ -479,6 +479,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         // Phase 2 (lanes along the channel axis): + residual, hi/lo split, 16-byte stores that cover
         // whole 32/64-byte row pieces (full sectors) instead of one 16-byte piece in each of 32 lines.
         const int ew = warp - (PW + 1);
+        const bool epi_leader = elect_one();           // the lane that issues this warp's TMA stores (and waits for them)
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         // tile_split: half of the warp sets serve accumulator 0, the other half accumulator 1
         const int nset_all = epi_warps >> 2;
@@ -509,7 +510,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                 for (int c0 = cset * 32; c0 < NT; c0 += 32 * nsets) {
                     const int gw = NT - c0 < 32 ? 16 : 32;         // NT is a multiple of 16
                     if (tma_out && gw != 32) {                      // the old path reuses the tile a TMA store may still be reading
-                        if (lane == 0) bulk_wait_group_read0();
+                        if (epi_leader) bulk_wait_group_read0();
                         __syncwarp();
                     }
                     for (int h = 0; h < gw; h += 16) {
@@ -554,7 +555,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         if (tma_out && gw == 32 && h == 0) {
                             // the TMA engine may still be reading this warp's tile (previous block): wait right before the
                             // first shared-memory store, after this block's TMEM loads and math are already done
-                            if (lane == 0) bulk_wait_group_read0();
+                            if (epi_leader) bulk_wait_group_read0();
                             __syncwarp();
                         }
                         if (tma_out && gw == 32 && !f32_out) {
@@ -582,7 +583,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                     if (tma_out && gw == 32) {
                         fence_proxy_async_smem();                  // generic-proxy tile writes -> visible to the TMA engine
                         __syncwarp();
-                        if (lane == 0) {
+                        if (epi_leader) {
                             const int row0 = sb * p.pix_per_seg + lp0;
                             if (f32_out) tma_store_2d(&p.omap, stg, n_tile * NT + c0, row0);
                             else tma_store_3d(&p.omap, stg, n_tile * NT + c0, row0, 0);
@@ -678,7 +679,7 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_acc_empty[a]);
         }
-        if (p.out_tma != 0 && lane == 0) bulk_wait_group0();     // shared memory must outlive the engine's reads
+        if (p.out_tma != 0 && epi_leader) bulk_wait_group0();     // shared memory must outlive the engine's reads
         if (prof && warp == PW + 1 && lane == 0) { p.prof[5] = pw0; p.prof[6] = (unsigned long long)(clock64() - prof_t0); }
     }
     tc_fence_before();
