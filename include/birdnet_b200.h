@@ -143,6 +143,11 @@ int bn_engine_clear_range_filter(bn_engine* engine);
 int bn_engine_run(bn_engine* engine, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
                   const bn_run_opts* opts, bn_outputs* out);
 int bn_ctx_create(bn_engine* engine, uint64_t max_batch_size, bn_ctx** out);
+/* bn_ctx_create with flags.  BN_CTX_ALLOW_PERCH lifts the reference's refusal of
+ * PerchV2 models (batch_context.rs:107-114): the staged context path then serves all four Perch outputs by index
+ * (embedding [0] and logits [3] in bn_outputs; spatial_embedding / spectrogram through bn_ctx_read_tensor). */
+enum { BN_CTX_ALLOW_PERCH = 1 };
+int bn_ctx_create_ex(bn_engine* engine, uint64_t max_batch_size, uint32_t flags, bn_ctx** out);
 void bn_ctx_destroy(bn_ctx* ctx);
 int bn_ctx_run(bn_ctx* ctx, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
                const bn_run_opts* opts, bn_outputs* out);

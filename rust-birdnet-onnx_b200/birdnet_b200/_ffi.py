@@ -26,6 +26,7 @@ BN_MAX_DIMS, BN_MAX_OUTPUTS = 8, 8
  BN_ERR_LABEL_PARSE, BN_ERR_INFERENCE, BN_ERR_INVALID_COORDINATES, BN_ERR_INVALID_DATE,
  BN_ERR_RANGE_FILTER_INFERENCE, BN_ERR_TIMEOUT, BN_ERR_CANCELLED, BN_ERR_RUNTIME_INIT) = range(17)
 BN_ERR_INVALID_ARGUMENT = 19
+BN_CTX_ALLOW_PERCH = 1          # bn_ctx_create_ex flag
 
 
 class DeviceCfg(C.Structure):
@@ -82,6 +83,7 @@ SIGNATURES = {
     "bn_engine_clear_range_filter": (C.c_int, [_vp]),
     "bn_engine_run": (C.c_int, [_vp, _P(_vp), _P(C.c_uint64), C.c_uint64, _P(RunOpts), _P(Outputs)]),
     "bn_ctx_create": (C.c_int, [_vp, C.c_uint64, _P(_vp)]),
+    "bn_ctx_create_ex": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _P(_vp)]),
     "bn_ctx_destroy": (None, [_vp]),
     "bn_ctx_run": (C.c_int, [_vp, _P(_vp), _P(C.c_uint64), C.c_uint64, _P(RunOpts), _P(Outputs)]),
     "bn_ctx_max_batch_size": (C.c_uint64, [_vp]),

@@ -336,9 +336,14 @@ class Classifier:
             return []
         return self._run_engine(segments, options)
 
-    def create_batch_context(self, max_batch_size: int) -> BatchInferenceContext:
+    def create_batch_context(self, max_batch_size: int, allow_perch: bool = False) -> BatchInferenceContext:
+        """classifier.rs:777-792.  `allow_perch=True` (not in the reference) lifts the PerchV2
+        refusal of batch_context.rs:107-114 and serves Perch through the same staged path."""
         h = C.c_void_p()
-        raise_for_status(_lib.bn_ctx_create(self._h, int(max_batch_size), C.byref(h)))
+        if allow_perch:
+            raise_for_status(_lib.bn_ctx_create_ex(self._h, int(max_batch_size), _ffi.BN_CTX_ALLOW_PERCH, C.byref(h)))
+        else:
+            raise_for_status(_lib.bn_ctx_create(self._h, int(max_batch_size), C.byref(h)))
         return BatchInferenceContext(self, h, int(max_batch_size))
 
     def predict_batch_with_context(self, context: BatchInferenceContext, segments: Sequence,

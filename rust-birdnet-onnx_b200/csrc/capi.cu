@@ -158,6 +158,12 @@ int bn_ctx_create(bn_engine* engine, uint64_t max_batch_size, bn_ctx** out) {
         return set_error(BN_ERR_INFERENCE, "BatchInferenceContext does not yet support PerchV2 models. Use predict_batch() instead.");
     return ctx_create(engine, max_batch_size, out);
 }
+int bn_ctx_create_ex(bn_engine* engine, uint64_t max_batch_size, uint32_t flags, bn_ctx** out) {
+    if (!engine || !out) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (flags & ~(uint32_t)BN_CTX_ALLOW_PERCH) return set_error(BN_ERR_INVALID_ARGUMENT, "unknown context flag");
+    if (!(flags & BN_CTX_ALLOW_PERCH)) return bn_ctx_create(engine, max_batch_size, out);
+    return ctx_create(engine, max_batch_size, out);
+}
 void bn_ctx_destroy(bn_ctx* ctx) { delete ctx; }
 
 int bn_ctx_run(bn_ctx* ctx, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,

@@ -424,6 +424,23 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         } else if (MODE != TC_IN_HALO && elect_one()) {
             const uint32_t idesc2 = umma_idesc_f16(TM, 2 * NT), idesc1 = umma_idesc_f16(TM, NT);
             const uint32_t a_kb = MODE == TC_IN_TMA ? (uint32_t)p.kb : 64u;
+            // everything that does not depend on the tile is formed once: stage s / chunk kc / K step j only ADD to the
+            // start-address field of a base descriptor (16-byte units; the whole ring lies below 256 KB)
+            const uint32_t stage16 = stage_bytes >> 4, w16 = w_bytes >> 4;
+            const uint64_t dA0 = MODE == TC_IN_TMA ? umma_desc_kmajor(smem_u32(tiles), a_kb * 2u) : umma_desc_sw128(smem_u32(tiles));
+            const uint64_t dW0 = w_res ? umma_desc_sw128(smem_u32(tiles0)) : umma_desc_sw128(smem_u32(tiles) + 2 * A_TILE_BYTES);
+            uint32_t dlt[4];                               // A start-address delta of K step j inside a chunk
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (MODE == TC_IN_TMA) {
+                    // A: K block of kb channels per sub-tile (kb = 64 -> one SWIZZLE_128B tile per chunk)
+                    const uint32_t kk = (uint32_t)j * 16u;
+                    const uint32_t sub = kk / a_kb, in_sub = kk - sub * a_kb;
+                    dlt[j] = ((sub * (uint32_t)TM * a_kb * 2u) >> 4) + (in_sub >> 3);
+                } else {
+                    dlt[j] = kDescKStep * (uint32_t)j;     // one SWIZZLE_128B [128][64] tile per plane
+                }
+            }
             if (w_res) mbar_wait(&bar_w, 0);
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -435,34 +452,17 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                     mbar_wait_t(&bar_full[s], ph, pw1, prof);
                     fence_proxy_async_smem();          // cp.async / st.shared (generic proxy) -> tcgen05 reads (async proxy)
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t db_hi = umma_desc_sw128(w_res ? smem_u32(tiles0) + (uint32_t)kc * w_bytes : a_hi + 2 * A_TILE_BYTES);   // [W_hi | W_lo]: 2NT rows
+                    const uint64_t da_s = dA0 + (uint64_t)(s * stage16);
+                    const uint64_t db_hi = w_res ? dW0 + (uint64_t)((uint32_t)kc * w16) : dW0 + (uint64_t)(s * stage16);   // [W_hi | W_lo]: 2NT rows
                     int ksteps = (p.K - kc * KC + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
-                    if (MODE != TC_IN_TMA) {
-                        // one SWIZZLE_128B [128][64] tile per plane: K step j = +2 in the start-address field
-                        const uint64_t da_hi = umma_desc_sw128(a_hi);
-                        const uint64_t da_lo = da_hi + (uint64_t)(A_TILE_BYTES >> 4);
-                        uint32_t accum = kc != 0 ? 1u : 0u;
 #pragma unroll 4
-                        for (int j = 0; j < ksteps; ++j) {
-                            const uint64_t adv = (uint64_t)(kDescKStep * j);
-                            umma_f16(acc, da_hi + adv, db_hi + adv, idesc2, accum);
-                            umma_f16(acc + (uint32_t)NT, da_lo + adv, db_hi + adv, idesc1, 1u);
-                            accum = 1u;
-                        }
-                    } else {
-                        for (int j = 0; j < ksteps; ++j) {
-                            // A: K block of kb channels per sub-tile (kb = 64 -> one SWIZZLE_128B tile per chunk)
-                            const uint32_t kk = (uint32_t)j * 16u;
-                            const uint32_t sub = kk / a_kb, in_sub = kk - sub * a_kb;
-                            const uint32_t a_off = sub * (uint32_t)TM * a_kb * 2u;
-                            const uint64_t da_hi = umma_desc_kmajor(a_hi + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
-                            const uint64_t da_lo = umma_desc_kmajor(a_hi + A_TILE_BYTES + a_off, a_kb * 2u) + (uint64_t)(in_sub >> 3);
-                            const uint64_t adv = (uint64_t)(kDescKStep * j);
-                            umma_f16(acc, da_hi, db_hi + adv, idesc2, (kc | j) != 0 ? 1u : 0u);
-                            if (!(p.debug_flags & 4)) umma_f16(acc + (uint32_t)NT, da_lo, db_hi + adv, idesc1, 1u);
-                        }
+                    for (int j = 0; j < ksteps; ++j) {
+                        const uint64_t da_hi = da_s + (uint64_t)dlt[j];
+                        const uint64_t db = db_hi + (uint64_t)(kDescKStep * j);
+                        umma_f16(acc, da_hi, db, idesc2, (kc | j) != 0 ? 1u : 0u);
+                        if (MODE != TC_IN_TMA || !(p.debug_flags & 4))
+                            umma_f16(acc + (uint32_t)NT, da_hi + (uint64_t)(A_TILE_BYTES >> 4), db, idesc1, 1u);
                     }
                     umma_commit(&bar_empty[s]);        // frees the smem stage when these MMAs retire
                     if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1u; }

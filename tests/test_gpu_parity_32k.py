@@ -139,6 +139,20 @@ def test_perch_matches_oracle_and_golden(perch):
         clf.create_batch_context(4)
     assert str(e.value) == ("inference failed: BatchInferenceContext does not yet support PerchV2 models. "
                             "Use predict_batch() instead.")
+    # opt-in context for Perch (bn_ctx_create_ex + BN_CTX_ALLOW_PERCH), same staged path, same bits;
+    # outputs 1 and 2 (which the reference ignores, classifier.rs:929-934) stay on the device unless asked for
+    ctx = clf.create_batch_context(10, allow_perch=True)
+    res2 = clf.predict_batch_with_context(ctx, list(audio))
+    for a, b in zip(res, res2):
+        assert np.array_equal(a.raw_scores, b.raw_scores) and np.array_equal(a.embeddings, b.embeddings)
+        assert [(p.index, p.confidence) for p in a.predictions] == [(p.index, p.confidence) for p in b.predictions]
+    orc = _oracle(spec, path)
+    keep = orc.forward(audio)
+    spat = ctx.read_tensor("spatial_embedding", 10)
+    assert spat.shape == (10, 16 * 4 * 1536)
+    ref_spat = np.asarray(keep["spatial_embedding"]).reshape(10, -1)
+    assert np.abs(spat[pinned] - ref_spat[pinned]).max() < 2e-3 * max(1.0, float(np.abs(ref_spat[pinned]).max()))   # un-pooled activations
+    assert ctx.read_tensor("spectrogram", 10).shape == (10, 500 * 128)
     with pytest.raises(bb.InputSize) as e:
         clf.predict(np.zeros(144000, dtype=np.float32))
     assert str(e.value) == "input size mismatch: expected 160000 samples, got 144000"
