@@ -88,9 +88,9 @@ struct bn_engine {
     // six ways; two lanes let one batch's tail / launch gaps / under-filled waves be covered by the other's kernels
     // (measured device-resident: 65.3 k -> 68.6 k segments/s).  H2D / D2H copies stay on their own streams and overlap
     // the lanes.  BN_COMPUTE_LANES=1|2; BN_SHARED_COMPUTE=0 gives every context a private compute stream.
-    static constexpr int MAX_LANES = 2;
+    static constexpr int MAX_LANES = 4;
     int n_lanes = 2;
-    cudaStream_t compute[MAX_LANES] = {nullptr, nullptr};
+    cudaStream_t compute[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     std::mutex launch_mu[MAX_LANES];
     std::atomic<int> next_lane{0};
     cudaStream_t h2d = nullptr;     // page-locked caller memory is copied on this one stream, in kernel order
