@@ -385,7 +385,8 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     }
     BN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     BN_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
-    BN_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    // blocking sync: several driver threads per GPU (and 8 ranks per box) wait here; they must sleep, not spin on the host cores
+    BN_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming | cudaEventBlockingSync));
     BN_CUDA(cudaEventCreateWithFlags(&c->ev_results, cudaEventDisableTiming));
     BN_CUDA(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
     BN_CUDA(cudaHostAlloc(&c->h_in, mb * S * sizeof(float), cudaHostAllocDefault));
