@@ -219,7 +219,9 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             tc_pack_weights(op.weight.data(), K, op.cout, op.ldw, d.nt, pack, &d.n_tiles, &d.k_chunks);
             d.stages = forced_stages > 1 ? forced_stages : tc_conv_pick_stages(d.nt, d.k_chunks, d.epi_warps);
             d.tmem_cols = 32;
-            while (d.tmem_cols < 4 * d.nt) d.tmem_cols <<= 1;      // 2 buffers x (main | correction)
+            // 2 buffers x (main | correction); narrow tiles with 16 epilogue warps get four buffers (k_tc_conv: n_acc)
+            { const char* ev = getenv("BN_TC_ACC4"); const bool acc4 = !(ev && ev[0] == '0') && d.nt <= 32 && d.epi_warps == 16;
+              while (d.tmem_cols < (acc4 ? 8 : 4) * d.nt) d.tmem_cols <<= 1; }
             BN_CUDA(cudaMalloc(&d.wpack, pack.size() * sizeof(uint16_t)));
             BN_CUDA(cudaMemcpy(d.wpack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
             d.use_tc = true;

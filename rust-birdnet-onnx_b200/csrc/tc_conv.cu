@@ -84,8 +84,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES];
     __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];
-    __shared__ __align__(8) uint64_t bar_acc_full[2];
-    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_acc_full[4];
+    __shared__ __align__(8) uint64_t bar_acc_empty[4];
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(8) uint64_t bar_w;         // HALO: resident weights landed
     __shared__ __align__(8) uint64_t halo_db[18];
@@ -100,6 +100,10 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     // narrow tiles (NT <= 32) with 8 epilogue warps: the per-tile epilogue is a latency chain, so the two
     // warp sets take alternate tiles (accumulator a <-> set a) instead of splitting the few columns
     const bool tile_split = epi_warps >= 8 && NT <= 32;
+    // accumulators in TMEM: two, or four when the tiles are narrow and every one of the four epilogue warp sets can own
+    // one (a set then serves every fourth tile: the MMA thread no longer waits for a free accumulator)
+    const uint32_t acc_shift = (tile_split && epi_warps >= 16 && p.tmem_cols >= 8 * NT) ? 2u : 1u;
+    const uint32_t n_acc = 1u << acc_shift;
     const bool prof = p.prof != nullptr && blockIdx.x == 0;
     unsigned long long pw0 = 0, pw1 = 0;
     const long long prof_t0 = prof ? clock64() : 0;
@@ -117,9 +121,9 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             mbar_init(&bar_empty[s], 1);       // tcgen05.commit
         }
         mbar_init(&bar_w, 1);
-        for (int a = 0; a < 2; ++a) {
+        for (uint32_t a = 0; a < n_acc; ++a) {
             mbar_init(&bar_acc_full[a], 1);    // tcgen05.commit
-            mbar_init(&bar_acc_empty[a], tile_split ? (uint32_t)(epi_warps >> 1) : (uint32_t)epi_warps);   // one arrive per epilogue warp serving it
+            mbar_init(&bar_acc_empty[a], tile_split ? (uint32_t)epi_warps >> acc_shift : (uint32_t)epi_warps);   // one arrive per epilogue warp serving it
         }
         fence_barrier_init();
     }
@@ -401,8 +405,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             mbar_wait(&bar_w, 0);
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const uint32_t a = it & 1u;
-                mbar_wait_t(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u, pw0, prof);
+                const uint32_t a = it & (n_acc - 1u);
+                mbar_wait_t(&bar_acc_empty[a], ((it >> acc_shift) & 1u) ^ 1u, pw0, prof);
                 mbar_wait_t(&bar_full[s], ph, pw1, prof);
                 fence_proxy_async_smem();
                 tc_fence_after();
@@ -444,8 +448,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             if (w_res) mbar_wait(&bar_w, 0);
             uint32_t s = 0, ph = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-                const uint32_t a = it & 1u;
-                mbar_wait_t(&bar_acc_empty[a], ((it >> 1) & 1u) ^ 1u, pw0, prof);
+                const uint32_t a = it & (n_acc - 1u);
+                mbar_wait_t(&bar_acc_empty[a], ((it >> acc_shift) & 1u) ^ 1u, pw0, prof);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + a * 2u * (uint32_t)NT;
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -483,9 +487,10 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         // tile_split: half of the warp sets serve accumulator 0, the other half accumulator 1
         const int nset_all = epi_warps >> 2;
-        const int wset = tile_split ? (ew >> 2) / (nset_all >> 1) : 0;
-        const int cset = tile_split ? (ew >> 2) % (nset_all >> 1) : (ew >> 2);
-        const int nsets = tile_split ? (nset_all >> 1) : nset_all;
+        const int sets_per_acc = tile_split ? nset_all >> acc_shift : nset_all;
+        const int wset = tile_split ? (ew >> 2) / sets_per_acc : 0;
+        const int cset = tile_split ? (ew >> 2) % sets_per_acc : (ew >> 2);
+        const int nsets = sets_per_acc;
         float* stg = reinterpret_cast<float*>(tiles + ring_bytes + (size_t)ew * EPI_STAGE_BYTES);
         uint32_t it = 0;
         const bool vec = (p.cout & 15) == 0;           // every 16-column group is full and 16-byte aligned
@@ -496,9 +501,9 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
             const int sb = mt / p.tiles_per_seg, lt = mt - sb * p.tiles_per_seg;
             const int lp0 = lt * TM + q * 32;                  // first row of this warp inside the segment
             const int lp = lp0 + lane;
-            const uint32_t a = it & 1u;
+            const uint32_t a = it & (n_acc - 1u);
             if (tile_split && (int)a != wset) continue;
-            mbar_wait_t(&bar_acc_full[a], (it >> 1) & 1u, pw0, prof && warp == PW + 1);
+            mbar_wait_t(&bar_acc_full[a], (it >> acc_shift) & 1u, pw0, prof && warp == PW + 1);
             tc_fence_after();
             const int row = sb * p.pix_per_seg + lp;
             const bool row_ok = lp < p.pix_per_seg && row < p.M;
