@@ -208,7 +208,8 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             const char* env_halo = getenv("BN_DISABLE_HALO");
             if (!(env_halo && env_halo[0] == '1') && op.kind == OP_CONV && op.in_scale < 0) {
                 const int c16 = (op.cout + 15) / 16 * 16;
-                for (int nt = d.nt; nt >= 16; nt -= 16) {
+                static const int halo_nt_max = [] { const char* ev = getenv("BN_HALO_NT_MAX"); return ev ? atoi(ev) : 128; }();
+                for (int nt = std::min(d.nt, halo_nt_max); nt >= 16; nt -= 16) {
                     if (c16 % nt) continue;
                     const int slots = tc_conv_halo_slots(op.k, op.stride, op.pad, op.cin, op.wout, op.win, nt, (K + 63) / 64, epi_rule(op.k, nt));
                     if (slots >= 2) { d.nt = nt; d.halo_slots = slots; break; }
