@@ -120,6 +120,34 @@ def _ncu_traffic():
         return {}, None
 
 
+def _bind_near_gpu(gpu_index: int):
+    """Keep this rank's threads (and therefore the page-locked buffers they allocate and fill) on the NUMA node the GPU
+    hangs off: on a two-socket box half of the ranks would otherwise stage their input through the other socket.
+    Returns the node, or None when the box has one node / the information is missing; never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        with open(f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 4 or len(cpus) == len(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def _dist():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,6 +280,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa_node = _bind_near_gpu(local) if world > 1 else None      # several ranks per box: each stays beside its GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -430,7 +459,7 @@ def run_ours(args):
                                    "BatchInferenceContext: front-end + CNN + fused top-k epilogue (BASELINE.json configs[1])",
                        "global_batch": B * world, "segment_samples": 144000, "top_k": 5, "min_confidence": 0.1,
                        "l2_policy": "inputs larger than L2 (147 MB batch > 126 MB L2)",
-                       "compute_lanes": len(lanes),
+                       "compute_lanes": len(lanes), "numa_node": numa_node,
                        "parallelism": f"{world} independent per-GPU shards, no collective",
                        "precision_policy": "FP32-equivalent (see DESIGN.md)",
                        "e2e_pipeline_depth": depth, "e2e_runs": "median of 5 runs of %d batches" % n_e2e, "e2e_run_values": run_log, "host_gc": "gc.freeze() after start-up", "host_cores": os.cpu_count(), "host_pack_threads_per_call": pack_threads},
