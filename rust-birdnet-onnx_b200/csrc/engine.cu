@@ -335,7 +335,9 @@ bn_engine::~bn_engine() {
 
 bn_ctx::~bn_ctx() {
     if (!eng) return;
-    cudaSetDevice(eng->device);
+    // everything below works from this context's own copies: a context destroyed after its engine (interpreter
+    // shutdown can do that to a binding) only gets CUDA errors back for the engine-owned lane, never a stale pointer
+    cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     if (in_stream && in_stream != stream) cudaStreamSynchronize(in_stream);
     if (copy_stream) cudaStreamSynchronize(copy_stream);
@@ -347,7 +349,7 @@ bn_ctx::~bn_ctx() {
     if (d_minmax) cudaFree(d_minmax);
     for (auto* x : d_xp) if (x) cudaFree(x);
     for (size_t i = 0; i < d_tensor.size(); ++i)
-        if (d_tensor[i] && eng->plan.tensors[i].alias_of < 0 && eng->plan.tensors[i].scale_base < 0) cudaFree(d_tensor[i]);
+        if (d_tensor[i] && i < owns_tensor.size() && owns_tensor[i]) cudaFree(d_tensor[i]);
     if (h_logits) cudaFreeHost(h_logits);
     if (h_emb) cudaFreeHost(h_emb);
     if (d_topk) cudaFree(d_topk);
@@ -372,6 +374,7 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     BN_CUDA(cudaSetDevice(e->device));
     std::unique_ptr<bn_ctx> c(new bn_ctx());
     c->eng = e;
+    c->device = e->device;
     c->max_batch = max_batch;
     const Plan& p = e->plan;
     const size_t S = (size_t)p.sample_count;
@@ -404,10 +407,12 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
         c->d_xp.push_back(x);
     }
     c->d_tensor.assign(p.tensors.size(), nullptr);
+    c->owns_tensor.assign(p.tensors.size(), 0);
     for (size_t i = 0; i < p.tensors.size(); ++i) {
         const TensorInfo& t = p.tensors[i];
         if (t.alias_of >= 0 || t.scale_base >= 0) continue;
         BN_CUDA(cudaMalloc(&c->d_tensor[i], mb * t.elems() * sizeof(float)));
+        c->owns_tensor[i] = 1;
     }
     for (size_t i = 0; i < p.tensors.size(); ++i)
         if (p.tensors[i].alias_of >= 0) c->d_tensor[i] = c->d_tensor[p.root((int)i)];

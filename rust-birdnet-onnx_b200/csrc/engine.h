@@ -100,6 +100,8 @@ struct bn_engine {
 
 struct bn_ctx {
     bn_engine* eng = nullptr;
+    int device = 0;                     // copy of eng->device: the destructor does not touch the engine
+    std::vector<uint8_t> owns_tensor;   // per plan tensor: this context allocated it (not an alias / virtual tensor)
     uint64_t max_batch = 0;
     cudaStream_t stream = nullptr;      // compute: one of the engine's lanes (shared) or a private stream
     int lane = 0;
