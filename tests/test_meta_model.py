@@ -17,6 +17,9 @@ SCORE_TOL = 2e-6      # f32 dot products of <= 256 terms in a different summatio
 PLACES = [(60.17, 24.94, 6, 15), (-33.87, 151.21, 12, 31), (0.0, 0.0, 1, 1), (90.0, -180.0, 2, 8), (-90.0, 180.0, 7, 22)]
 
 
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meta_seed0.npz"))
+
+
 def _weights(path):
     from oracle.model_oracle import load_initializers
     return load_initializers(path)
@@ -76,6 +79,20 @@ def test_range_filter_builder_required_fields_and_no_cpu_fallback(has_gpu):
         rf.predict(0.0, 0.0, 1, 1)
 
 
+def test_meta_oracle_against_committed_golden():
+    """tests/golden/meta_seed0.npz (tests/golden/make_golden_meta.py) pins the stand-in model file and the oracle."""
+    import hashlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meta_seed0.npz"))
+    path = mm.ensure_meta_model(6522, 0)
+    assert hashlib.sha256(open(path, "rb").read()).digest() == bytes(g["model_sha256"])
+    w = _weights(path)
+    for i, (lat, lon, month, day) in enumerate(g["places"]):
+        s = mo.forward(w, np.float32(lat), np.float32(lon), np.float32(mo.calculate_week(int(month), int(day))))
+        assert np.abs(s[::8] - g["scores_every_8"][i]).max() <= 1e-6
+        assert int(s.argmax()) == int(g["argmax"][i])
+        assert abs(int((s >= np.float32(0.01)).sum()) - int(g["n_above_default_threshold"][i])) <= 2
+
+
 # ------------------------------------------------------------------ GPU: parity through the C ABI
 @pytest.fixture(scope="module")
 def meta_path():
@@ -100,6 +117,8 @@ def test_meta_scores_match_oracle(meta_path):
             assert _ffi.lib.bn_meta_predict(h, lat, lon, week, got.ctypes.data_as(C.POINTER(C.c_float)), 6522) == 0
             ref = mo.forward(w, np.float32(lat), np.float32(lon), np.float32(week))
             assert np.abs(got - ref).max() <= SCORE_TOL
+            gi = [tuple(p) for p in GOLD["places"]].index((lat, lon, month, day))
+            assert np.abs(got[::8] - GOLD["scores_every_8"][gi]).max() <= SCORE_TOL      # committed fixture
         short = np.empty(10, dtype=np.float32)
         assert _ffi.lib.bn_meta_predict(h, 0.0, 0.0, 1.0, short.ctypes.data_as(C.POINTER(C.c_float)), 10) != 0
     finally:
