@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 
 using namespace bn;
 
@@ -25,6 +26,7 @@ struct bn_meta {
     float* d_in = nullptr;
     float* h_scores = nullptr;                 // pinned
     cudaStream_t stream = nullptr;
+    std::mutex mu;                             // the reference keeps its session in a Mutex (src/rangefilter.rs:271, 390, 461-466)
     ~bn_meta() {
         cudaSetDevice(device);
         for (auto& l : layers) { if (l.w) cudaFree(l.w); if (l.b) cudaFree(l.b); }
@@ -182,6 +184,7 @@ static int meta_forward(bn_meta* m, float latitude, float longitude, float week,
 int bn_meta_predict(bn_meta* m, float latitude, float longitude, float week, float* scores, uint64_t n) {
     if (!m || !scores) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
     if (n != (uint64_t)m->n_out) return set_error(BN_ERR_INVALID_ARGUMENT, "scores buffer must hold " + std::to_string(m->n_out) + " floats");
+    std::lock_guard<std::mutex> run_lock(m->mu);
     const float* d = nullptr;
     int st = meta_forward(m, latitude, longitude, week, &d);
     if (st != BN_OK) return st;
@@ -200,6 +203,7 @@ int bn_meta_install_range_filter(bn_meta* m, bn_engine* engine, float latitude, 
     if (m->device != engine->device) return set_error(BN_ERR_INVALID_ARGUMENT, "meta model and engine live on different devices");
     if ((uint64_t)m->n_out != (uint64_t)engine->plan.num_species)
         return set_error(BN_ERR_INFERENCE, "meta model has " + std::to_string(m->n_out) + " classes, model has " + std::to_string(engine->plan.num_species));
+    std::lock_guard<std::mutex> run_lock(m->mu);
     const float* d = nullptr;
     int st = meta_forward(m, latitude, longitude, week, &d);
     if (st != BN_OK) return st;
