@@ -6,8 +6,9 @@
  * Plain C: opaque handles, pointers and sizes only.  Every function returns a bn_status
  * (0 = ok); the message of the last failure on the calling thread is bn_last_error().
  *
- * Threading: a bn_engine may be shared by threads (runs through bn_engine_run serialise on an
- * internal lock, like the reference's Mutex<Session>, src/classifier.rs:435); a bn_ctx is
+ * Threading: a bn_engine may be shared by threads (concurrent bn_engine_run calls each check out one of
+ * up to four internal contexts and queue when all are busy - the reference serialises on its
+ * Mutex<Session>, src/classifier.rs:435); a bn_ctx is
  * single-threaded, one per thread (src/batch_context.rs:56-60).
  */
 #ifndef BIRDNET_B200_H
@@ -139,7 +140,10 @@ int bn_engine_clear_range_filter(bn_engine* engine);
  * bn_ctx_create <- BatchInferenceContext::new / session.create_binding (batch_context.rs:102-133)
  * bn_ctx_run    <- prepare_input + bind_outputs_to_device + run_binding_with_options +
  *                  synchronize + extract_outputs (batch_context.rs:188-338, classifier.rs:839-865)
- * seg_lens[i] is the sample count of segment i (slices carry their length in Rust). */
+ * seg_lens[i] is the sample count of segment i (slices carry their length in Rust).
+ * bn_engine_run takes a batch of ANY size (like predict_batch): it runs chunks of <= 256 segments on one of a small
+ * bounded pool of internal contexts and gathers the results in a per-thread host buffer; the pointers in `out`
+ * stay valid until the calling thread's next bn_engine_run. */
 int bn_engine_run(bn_engine* engine, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
                   const bn_run_opts* opts, bn_outputs* out);
 int bn_ctx_create(bn_engine* engine, uint64_t max_batch_size, bn_ctx** out);
@@ -176,6 +180,11 @@ int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems);
 /* Kernel launches enqueued by the last run on this ctx, and per-stage device times (ms) of the
  * last run when profiling was enabled with bn_ctx_set_profiling(ctx, 1). */
 uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx);
+/* Segments of the last completed run on this ctx whose logits were not all finite.  The tensor-core path keeps
+ * operands as fp16 hi + fp16 lo pairs: ~22 mantissa bits but the fp16 RANGE, so an activation beyond +-65504 turns
+ * into NaN downstream (weights beyond it are refused at load time with BN_ERR_MODEL_LOAD).  The run still returns
+ * BN_OK - the reference also returns NaN scores for NaN input - this counter lets a caller tell. */
+uint64_t bn_ctx_nonfinite_segments(const bn_ctx* ctx);
 int bn_ctx_set_profiling(bn_ctx* ctx, int32_t enabled);
 int bn_ctx_stage_times(const bn_ctx* ctx, float* ms_out, char (*names_out)[48], uint64_t cap, uint64_t* n_out);
 void* bn_ctx_stream(bn_ctx* ctx);                      /* cudaStream_t the kernels run on */

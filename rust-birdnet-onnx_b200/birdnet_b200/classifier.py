@@ -219,6 +219,10 @@ class BatchInferenceContext:
     def last_launch_count(self) -> int:
         return int(_lib.bn_ctx_last_launch_count(self._h))
 
+    def nonfinite_segments(self) -> int:
+        """Segments of the last run whose logits were not all finite (see bn_ctx_nonfinite_segments)."""
+        return int(_lib.bn_ctx_nonfinite_segments(self._h))
+
     # ---- introspection used by the parity tests and bench.py ------------------------------
     def read_tensor(self, name: str, batch: int) -> np.ndarray:
         """Intermediate tensor of the last run, NHWC, flattened per segment: [batch, elems]."""

@@ -6,6 +6,15 @@
 
 using namespace bn;
 
+namespace {
+struct DevBuf {                 // freed on every exit path of the *_apply helpers
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+}  // namespace
+
 extern "C" {
 
 const char* bn_last_error(void) { return last_error().c_str(); }
@@ -51,6 +60,9 @@ int bn_detect_model_type(const int64_t* input_dims, int32_t input_rank, const in
                          const int32_t* output_ranks, int32_t n_outputs, int32_t model_type_override,
                          bn_io_info* out) {
     if (!out || (input_rank > 0 && !input_dims)) return set_error(BN_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_outputs < 0 || (n_outputs > 0 && (!output_ranks || !output_dims))) return set_error(BN_ERR_INVALID_ARGUMENT, "null output shape arrays");
+    for (int i = 0; i < n_outputs; ++i)
+        if (output_ranks[i] < 0 || output_ranks[i] > BN_MAX_DIMS) return set_error(BN_ERR_INVALID_ARGUMENT, "output rank out of range");
     std::vector<int64_t> in(input_dims, input_dims + std::max(0, input_rank));
     std::vector<std::vector<int64_t>> outs;
     const int64_t* p = output_dims;
@@ -119,23 +131,74 @@ int bn_engine_clear_range_filter(bn_engine* engine) {
     return BN_OK;
 }
 
-// one context per calling thread, grown on demand (predict_batch allocates per call in the
-// reference: classifier.rs:701-710)
-static int thread_ctx_for(bn_engine* e, uint64_t batch, bn_ctx** out) {
-    std::lock_guard<std::mutex> lk(e->ctx_mu);
-    auto id = std::this_thread::get_id();
-    auto it = e->thread_ctx.find(id);
-    if (it != e->thread_ctx.end() && it->second->max_batch >= batch) { *out = it->second; return BN_OK; }
-    uint64_t cap = 1;
-    while (cap < batch) cap <<= 1;
-    if (it != e->thread_ctx.end()) { delete it->second; e->thread_ctx.erase(it); }
+// bn_engine_run (predict / predict_batch, classifier.rs:676-727): a small bounded pool of internal contexts that
+// are checked out per call and returned, and a chunk loop, so that
+//   * a call of any size works in bounded device memory (the reference's predict_batch takes any batch),
+//   * services that churn threads do not accumulate one context per thread id ever seen,
+//   * a context is only replaced by a larger one AFTER the larger one exists.
+// Results of all chunks are gathered in a per-thread host buffer that stays valid until the same thread calls
+// bn_engine_run again (the pooled context itself goes straight back to the pool).
+namespace {
+constexpr uint64_t RUN_CHUNK = 256;       // segments per internal context (about 3 GB of activations for v2.4)
+
+struct HostResults {
+    std::vector<float> logits, emb;
+    std::vector<bn_pred> topk;
+    std::vector<uint32_t> count;
+};
+thread_local HostResults t_results;
+
+struct CtxLease {
+    bn_engine* e;
     bn_ctx* c = nullptr;
-    int st = ctx_create(e, cap, &c);
-    if (st != BN_OK) return st;
-    e->thread_ctx[id] = c;
-    *out = c;
-    return BN_OK;
+    explicit CtxLease(bn_engine* eng) : e(eng) {}
+    ~CtxLease() {
+        if (!c) return;
+        { std::lock_guard<std::mutex> lk(e->ctx_mu); e->run_free.push_back(c); }
+        e->ctx_cv.notify_one();
+    }
+};
+
+int checkout_ctx(bn_engine* e, uint64_t need, CtxLease& lease) {
+    uint64_t cap = 1;
+    while (cap < need) cap <<= 1;
+    std::unique_lock<std::mutex> lk(e->ctx_mu);
+    while (true) {
+        int best = -1;                       // smallest free context that is large enough
+        for (size_t i = 0; i < e->run_free.size(); ++i)
+            if (e->run_free[i]->max_batch >= need && (best < 0 || e->run_free[i]->max_batch < e->run_free[best]->max_batch)) best = (int)i;
+        if (best >= 0) {
+            lease.c = e->run_free[best];
+            e->run_free.erase(e->run_free.begin() + best);
+            return BN_OK;
+        }
+        if (e->run_created < bn_engine::MAX_RUN_CTX || !e->run_free.empty()) {
+            // room for one more, or a too-small free one to replace: build the new context first
+            bn_ctx* victim = nullptr;
+            if (e->run_created >= bn_engine::MAX_RUN_CTX) { victim = e->run_free.back(); e->run_free.pop_back(); }
+            else ++e->run_created;
+            lk.unlock();
+            bn_ctx* c = nullptr;
+            int st = ctx_create(e, cap, &c);
+            if (st != BN_OK && victim && victim->max_batch < cap) {
+                // out of memory with the small one still alive: free it and try once more
+                delete victim;
+                victim = nullptr;
+                st = ctx_create(e, cap, &c);
+                if (st != BN_OK) { lk.lock(); --e->run_created; return st; }
+            } else if (st != BN_OK) {
+                lk.lock();
+                if (victim) e->run_free.push_back(victim); else --e->run_created;
+                return st;
+            }
+            delete victim;
+            lease.c = c;
+            return BN_OK;
+        }
+        e->ctx_cv.wait(lk);                 // every internal context is busy: wait for one to come back
+    }
 }
+}  // namespace
 
 int bn_engine_run(bn_engine* engine, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t batch,
                   const bn_run_opts* opts, bn_outputs* out) {
@@ -146,10 +209,42 @@ int bn_engine_run(bn_engine* engine, const float* const* seg_ptrs, const uint64_
     const uint64_t S = engine->info.sample_count;
     for (uint64_t i = 0; i < batch; ++i)
         if (seg_lens[i] != S) return set_error_detail(BN_ERR_BATCH_INPUT_SIZE, "batch input size mismatch", i, S, seg_lens[i]);
-    bn_ctx* c = nullptr;
-    int st = thread_ctx_for(engine, batch, &c);
+    CtxLease lease(engine);
+    int st = checkout_ctx(engine, std::min(batch, RUN_CHUNK), lease);
     if (st != BN_OK) return st;
-    return ctx_run_host(c, seg_ptrs, seg_lens, batch, false, opts, out);
+    bn_ctx* c = lease.c;
+    HostResults& hr = t_results;
+    const uint64_t N = engine->info.num_species, E = engine->info.embedding_dim;
+    uint64_t k_stride = 0;
+    bool sized = false;
+    for (uint64_t lo = 0; lo < batch; lo += c->max_batch) {
+        const uint64_t nb = std::min<uint64_t>(c->max_batch, batch - lo);
+        bn_outputs part;
+        st = ctx_run_host(c, seg_ptrs + lo, seg_lens + lo, nb, false, opts, &part);
+        if (st != BN_OK) return st;
+        if (!sized) {                        // the first chunk fixes the top-k stride of the whole call
+            k_stride = part.topk_stride;
+            hr.logits.resize(batch * N);
+            hr.emb.resize(part.embeddings ? batch * E : 0);
+            hr.topk.resize(batch * k_stride);
+            hr.count.resize(batch);
+            sized = true;
+        }
+        memcpy(hr.logits.data() + lo * N, part.logits, nb * N * sizeof(float));
+        if (part.embeddings) memcpy(hr.emb.data() + lo * E, part.embeddings, nb * E * sizeof(float));
+        if (k_stride) memcpy(hr.topk.data() + lo * k_stride, part.topk, nb * k_stride * sizeof(bn_pred));
+        memcpy(hr.count.data() + lo, part.topk_count, nb * sizeof(uint32_t));
+    }
+    memset(out, 0, sizeof(*out));
+    out->batch = batch;
+    out->num_species = N;
+    out->logits = hr.logits.data();
+    out->embedding_dim = E;
+    out->embeddings = hr.emb.empty() ? nullptr : hr.emb.data();
+    out->topk_stride = k_stride;
+    out->topk_count = hr.count.data();
+    out->topk = hr.topk.data();
+    return BN_OK;
 }
 
 int bn_ctx_create(bn_engine* engine, uint64_t max_batch_size, bn_ctx** out) {
@@ -238,6 +333,9 @@ int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems) {
 }
 
 uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+uint64_t bn_ctx_nonfinite_segments(const bn_ctx* ctx) {
+    return ctx && ctx->h_count ? ctx->h_count[std::max<uint64_t>(ctx->max_batch, 1)] : 0;
+}
 int bn_ctx_set_profiling(bn_ctx* ctx, int32_t enabled) {
     if (!ctx) return set_error(BN_ERR_INVALID_ARGUMENT, "null ctx");
     ctx->profiling = enabled != 0;
@@ -256,6 +354,7 @@ int bn_ctx_stage_times(const bn_ctx* ctx, float* ms_out, char (*names_out)[48], 
 void* bn_ctx_stream(bn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int32_t bn_engine_compute_lanes(const bn_engine* engine) { return engine ? engine->n_lanes : 0; }
 
+
 int bn_range_filter_apply(bn_engine* engine, const bn_pred* in, const uint32_t* in_count, uint64_t rows,
                           uint64_t stride, const uint8_t* state, const float* score, uint64_t n, int32_t rerank,
                           bn_pred* out, uint32_t* out_count) {
@@ -268,20 +367,21 @@ int bn_range_filter_apply(bn_engine* engine, const bn_pred* in, const uint32_t* 
     BN_CUDA(init_kernels_for_device());
     std::shared_ptr<RangeDev> r;
     if (state) { int st = make_range(device, state, score, n, rerank, r); if (st != BN_OK) return st; }
-    Pred *d_in = nullptr, *d_out = nullptr;
-    uint32_t *d_ic = nullptr, *d_oc = nullptr;
+    DevBuf b_in, b_out, b_ic, b_oc;
     size_t bytes = rows * stride * sizeof(Pred);
-    BN_CUDA(cudaMalloc(&d_in, bytes));
-    BN_CUDA(cudaMalloc(&d_out, bytes));
-    BN_CUDA(cudaMalloc(&d_ic, rows * sizeof(uint32_t)));
-    BN_CUDA(cudaMalloc(&d_oc, rows * sizeof(uint32_t)));
+    BN_CUDA(b_in.alloc(bytes));
+    BN_CUDA(b_out.alloc(bytes));
+    BN_CUDA(b_ic.alloc(rows * sizeof(uint32_t)));
+    BN_CUDA(b_oc.alloc(rows * sizeof(uint32_t)));
+    Pred *d_in = b_in.as<Pred>(), *d_out = b_out.as<Pred>();
+    uint32_t *d_ic = b_ic.as<uint32_t>(), *d_oc = b_oc.as<uint32_t>();
     cudaError_t ce = cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMemcpy(d_ic, in_count, rows * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = launch_range_filter((const Pred*)d_in, d_ic, (int)rows, (int)stride, r ? r->state : nullptr, r ? r->score : nullptr,
                                                     (int)n, rerank ? 1 : 0, d_out, d_oc, 0);
     if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
     if (ce == cudaSuccess) ce = cudaMemcpy(out_count, d_oc, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ic); cudaFree(d_oc);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) return cuda_fail(ce, "bn_range_filter_apply");
     return BN_OK;
 }
@@ -299,12 +399,13 @@ int bn_topk_apply(bn_engine* engine, const float* logits, uint64_t rows, uint64_
     BN_CUDA(init_kernels_for_device());
     std::shared_ptr<RangeDev> r;
     if (state) { int st = make_range(device, state, score, n, rerank, r); if (st != BN_OK) return st; }
-    float* d_l = nullptr;
-    Pred* d_out = nullptr;
-    uint32_t* d_oc = nullptr;
-    BN_CUDA(cudaMalloc(&d_l, rows * n * sizeof(float)));
-    BN_CUDA(cudaMalloc(&d_out, rows * k * sizeof(Pred)));
-    BN_CUDA(cudaMalloc(&d_oc, rows * sizeof(uint32_t)));
+    DevBuf b_l, b_out, b_oc;
+    BN_CUDA(b_l.alloc(rows * n * sizeof(float)));
+    BN_CUDA(b_out.alloc(rows * k * sizeof(Pred)));
+    BN_CUDA(b_oc.alloc(rows * sizeof(uint32_t)));
+    float* d_l = b_l.as<float>();
+    Pred* d_out = b_out.as<Pred>();
+    uint32_t* d_oc = b_oc.as<uint32_t>();
     cudaError_t ce = cudaMemcpy(d_l, logits, rows * n * sizeof(float), cudaMemcpyHostToDevice);
     TopkParams tp{};
     tp.logits = d_l; tp.batch = (int)rows; tp.n = (int)n; tp.k = (uint32_t)k;
@@ -314,7 +415,7 @@ int bn_topk_apply(bn_engine* engine, const float* logits, uint64_t rows, uint64_
     if (ce == cudaSuccess) ce = launch_topk(tp, 0);
     if (ce == cudaSuccess) ce = cudaMemcpy(out, d_out, rows * k * sizeof(Pred), cudaMemcpyDeviceToHost);
     if (ce == cudaSuccess) ce = cudaMemcpy(out_count, d_oc, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-    cudaFree(d_l); cudaFree(d_out); cudaFree(d_oc);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) return cuda_fail(ce, "bn_topk_apply");
     return BN_OK;
 }

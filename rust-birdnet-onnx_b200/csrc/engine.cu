@@ -315,7 +315,7 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
 
 bn_engine::~bn_engine() {
     cudaSetDevice(device);
-    for (auto& kv : thread_ctx) delete kv.second;
+    for (auto* c : run_free) delete c;       // every lease has been returned by the time the engine is destroyed
     for (auto& d : dev_ops) {
         if (d.weight) cudaFree(d.weight);
         if (d.bias) cudaFree(d.bias);
@@ -418,8 +418,9 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
         if (p.tensors[i].alias_of >= 0) c->d_tensor[i] = c->d_tensor[p.root((int)i)];
     BN_CUDA(cudaHostAlloc(&c->h_logits, mb * p.num_species * sizeof(float), cudaHostAllocDefault));
     if (p.embedding_dim > 0) BN_CUDA(cudaHostAlloc(&c->h_emb, mb * p.embedding_dim * sizeof(float), cudaHostAllocDefault));
-    BN_CUDA(cudaMalloc(&c->d_count, mb * sizeof(uint32_t)));
-    BN_CUDA(cudaHostAlloc(&c->h_count, mb * sizeof(uint32_t), cudaHostAllocDefault));
+    BN_CUDA(cudaMalloc(&c->d_count, (mb + 1) * sizeof(uint32_t)));          // [mb] per-segment counts + the non-finite counter
+    BN_CUDA(cudaHostAlloc(&c->h_count, (mb + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+    c->h_count[mb] = 0;
     *out = c.release();
     return BN_OK;
 }
@@ -831,6 +832,10 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     tp.rerank = post.range ? post.range->rerank : 0;
     tp.out = c->d_topk;
     tp.out_count = c->d_count;
+    // d_count[max_batch] counts the segments of this run whose logits are not all finite (an activation that left the
+    // fp16 range of the hi/lo operand format turns into NaN downstream; NaN audio does the same in the reference)
+    tp.nonfinite = c->d_count + std::max<uint64_t>(c->max_batch, 1);
+    BN_CUDA(cudaMemsetAsync(tp.nonfinite, 0, sizeof(uint32_t), s));
     BN_CUDA(launch_topk(tp, s));
     ++launches;
     prof_mark(c, "d2h");
@@ -853,6 +858,8 @@ static int enqueue_fetch(bn_ctx* c, int B, uint64_t k_eff) {
         BN_CUDA(cudaMemcpyAsync(c->h_emb, c->d_tensor[p.embedding_tensor], (size_t)B * p.embedding_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (k_eff > 0) BN_CUDA(cudaMemcpyAsync(c->h_topk, c->d_topk, (size_t)B * k_eff * sizeof(Pred), cudaMemcpyDeviceToHost, s));
     BN_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, (size_t)B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    { const size_t mb = std::max<uint64_t>(c->max_batch, 1);
+      BN_CUDA(cudaMemcpyAsync(c->h_count + mb, c->d_count + mb, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)); }
     if (!c->profiling) {
         BN_CUDA(cudaEventRecord(c->ev_fetched, s));
         c->fetch_pending = true;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -81,8 +82,12 @@ struct bn_engine {
     } fe_lm;
     std::mutex post_mu;
     bn::PostCfg post;
+    // bn_engine_run: bounded pool of internal contexts, checked out per call and returned (capi.cu)
+    static constexpr int MAX_RUN_CTX = 4;
     std::mutex ctx_mu;
-    std::map<std::thread::id, bn_ctx*> thread_ctx;   // bn_engine_run: one context per calling thread
+    std::condition_variable ctx_cv;
+    std::vector<bn_ctx*> run_free;
+    int run_created = 0;
     // Compute lanes of the engine: every context's kernels go to one of these streams (contexts alternate), one whole
     // batch at a time (launch_mu), so batches of concurrent callers run back to back instead of time-slicing the SMs
     // six ways; two lanes let one batch's tail / launch gaps / under-filled waves be covered by the other's kernels

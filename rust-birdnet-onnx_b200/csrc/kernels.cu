@@ -1257,9 +1257,12 @@ __device__ void filter_and_emit(uint32_t* s_idx, float* s_conf, unsigned long lo
     if (threadIdx.x == 0) *out_count = (uint32_t)cnt;
 }
 
-__global__ void __launch_bounds__(1024) k_topk(TopkParams p, int P) {
+// ws == nullptr: key / index / confidence arrays in dynamic shared memory (next_pow2(n)*8 + k*8 bytes must fit);
+// otherwise they live in the global workspace ws, (P*8 + k*8) bytes per row (any n, any k: postprocess.rs:50 has no limit)
+__global__ void __launch_bounds__(1024) k_topk(TopkParams p, int P, unsigned char* ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned char* base_mem = ws ? ws + (size_t)blockIdx.x * ((size_t)P * 8 + (size_t)p.k * 8) : smem_raw;
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(base_mem);
     uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_keys + P);
     float* s_conf = reinterpret_cast<float*>(s_idx + p.k);
     __shared__ int s_warp[33];
@@ -1269,8 +1272,16 @@ __global__ void __launch_bounds__(1024) k_topk(TopkParams p, int P) {
         if (threadIdx.x == 0) p.out_count[b] = 0;
         return;
     }
-    for (int i = threadIdx.x; i < P; i += blockDim.x)
-        s_keys[i] = i < p.n ? (((unsigned long long)total_order_key(lg[i]) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+    int bad = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const float x = i < p.n ? lg[i] : 0.f;
+        bad |= !isfinite(x);
+        s_keys[i] = i < p.n ? (((unsigned long long)total_order_key(x) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+    }
+    if (p.nonfinite) {
+        bad = __syncthreads_or(bad);
+        if (bad && threadIdx.x == 0) atomicAdd(p.nonfinite, 1u);
+    }
     bitonic_sort_desc(s_keys, P);
     // sigmoid on the k survivors, min_confidence: survivors stay in logit-descending order,
     // which is confidence-descending because sigmoid is monotone (ties: higher logit first)
@@ -1298,7 +1309,7 @@ __global__ void __launch_bounds__(1024) k_topk(TopkParams p, int P) {
 }
 
 __global__ void k_range_filter(const Pred* in, const uint32_t* in_count, int stride, const uint8_t* state,
-                               const float* score, int n, int rerank, Pred* out, uint32_t* out_count, int P);
+                               const float* score, int n, int rerank, Pred* out, uint32_t* out_count, int P, unsigned char* ws);
 
 // Small-k path (k <= 32): k rounds of block-wide arg-max over register-resident keys instead of a
 // full sort.  Keys are (total-order(logit) << 32 | ~index), so every key is unique and the order
@@ -1315,10 +1326,17 @@ __global__ void __launch_bounds__(1024) k_topk_small(TopkParams p) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const float* lg = p.logits + (size_t)b * p.n;
     unsigned long long keys[TOPK_SMALL_EPT];
+    int bad = 0;
 #pragma unroll
     for (int j = 0; j < TOPK_SMALL_EPT; ++j) {
         const int i = tid + j * blockDim.x;
-        keys[j] = i < p.n ? (((unsigned long long)total_order_key(lg[i]) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+        const float x = i < p.n ? lg[i] : 0.f;
+        bad |= !isfinite(x);
+        keys[j] = i < p.n ? (((unsigned long long)total_order_key(x) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+    }
+    if (p.nonfinite) {            // a segment whose logits are not all finite: bn_ctx_nonfinite_segments()
+        bad = __syncthreads_or(bad);
+        if (bad && tid == 0) atomicAdd(p.nonfinite, 1u);
     }
     for (uint32_t r = 0; r < p.k; ++r) {
         unsigned long long m = 0ull;
@@ -1390,17 +1408,28 @@ cudaError_t launch_topk(const TopkParams& p, cudaStream_t stream) {
     }
     const int P = next_pow2(p.n < 2 ? 2 : p.n);
     size_t smem = (size_t)P * 8 + (size_t)p.k * 8;
-    if (smem > (size_t)kMaxSortSmem) return cudaErrorInvalidValue;
     int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
-    k_topk<<<p.batch, threads, smem, stream>>>(p, P);
+    if (smem > (size_t)kMaxSortSmem) {
+        // too large for shared memory (n > 16 K with k > 32, or n > 32 K): same kernel over a stream-ordered global
+        // workspace.  Slower (the sort runs out of L2), but the reference's top_k_predictions has no size limit.
+        unsigned char* ws = nullptr;
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), smem * (size_t)p.batch, stream);
+        if (e != cudaSuccess) return e;
+        k_topk<<<p.batch, threads, 0, stream>>>(p, P, ws);
+        e = cudaGetLastError();
+        const cudaError_t e2 = cudaFreeAsync(ws, stream);
+        return e != cudaSuccess ? e : e2;
+    }
+    k_topk<<<p.batch, threads, smem, stream>>>(p, P, nullptr);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) k_range_filter(const Pred* in, const uint32_t* in_count, int stride,
                                                       const uint8_t* state, const float* score, int n, int rerank,
-                                                      Pred* out, uint32_t* out_count, int P) {
+                                                      Pred* out, uint32_t* out_count, int P, unsigned char* ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned char* base_mem = ws ? ws + (size_t)blockIdx.x * ((size_t)P * 8 + (size_t)stride * 8) : smem_raw;
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(base_mem);
     uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_keys + P);
     float* s_conf = reinterpret_cast<float*>(s_idx + stride);
     __shared__ int s_warp[33];
@@ -1422,8 +1451,16 @@ cudaError_t launch_range_filter(const Pred* in, const uint32_t* in_count, int ro
     if (rows <= 0 || stride <= 0) return cudaSuccess;
     const int P = next_pow2(stride < 2 ? 2 : stride);
     size_t smem = (size_t)P * 8 + (size_t)stride * 8;
-    if (smem > (size_t)kMaxSortSmem) return cudaErrorInvalidValue;
-    k_range_filter<<<rows, 256, smem, stream>>>(in, in_count, stride, state, score, n, rerank, out, out_count, P);
+    if (smem > (size_t)kMaxSortSmem) {             // lists longer than ~14 K entries: global workspace (see launch_topk)
+        unsigned char* ws = nullptr;
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&ws), smem * (size_t)rows, stream);
+        if (e != cudaSuccess) return e;
+        k_range_filter<<<rows, 256, 0, stream>>>(in, in_count, stride, state, score, n, rerank, out, out_count, P, ws);
+        e = cudaGetLastError();
+        const cudaError_t e2 = cudaFreeAsync(ws, stream);
+        return e != cudaSuccess ? e : e2;
+    }
+    k_range_filter<<<rows, 256, smem, stream>>>(in, in_count, stride, state, score, n, rerank, out, out_count, P, nullptr);
     return cudaGetLastError();
 }
 

@@ -172,6 +172,7 @@ struct TopkParams {
     int rerank;
     Pred* out;                  // [B][k]
     uint32_t* out_count;        // [B]
+    uint32_t* nonfinite;        // optional counter: += 1 per segment whose logits contain NaN / inf
 };
 cudaError_t launch_topk(const TopkParams& p, cudaStream_t stream);
 

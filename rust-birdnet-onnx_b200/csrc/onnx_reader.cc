@@ -62,37 +62,74 @@ bool next_field(Cursor& c, Field& f) {
     return true;
 }
 
-std::string str(const Field& f) { return std::string((const char*)f.data, f.len); }
-float f32_of(const Field& f) { float v; memcpy(&v, f.data, 4); return v; }
+// The file is untrusted: every accessor checks the wire type before it touches f.data / f.varint.
+std::string str(const Field& f) {
+    if (f.wt != 2) throw std::runtime_error("onnx: string field " + std::to_string(f.num) + " has wire type " + std::to_string(f.wt));
+    return std::string((const char*)f.data, f.len);
+}
+float f32_of(const Field& f) {
+    if (f.wt != 5 || f.len != 4) throw std::runtime_error("onnx: float field " + std::to_string(f.num) + " has wire type " + std::to_string(f.wt));
+    float v;
+    memcpy(&v, f.data, 4);
+    return v;
+}
+uint64_t varint_of(const Field& f) {
+    if (f.wt != 0) throw std::runtime_error("onnx: integer field " + std::to_string(f.num) + " has wire type " + std::to_string(f.wt));
+    return f.varint;
+}
+void packed_floats(const Field& f, std::vector<float>& out) {
+    if (f.wt == 2) {
+        if (f.len % 4) throw std::runtime_error("onnx: packed float field length is not a multiple of 4");
+        for (size_t i = 0; i < f.len; i += 4) { float v; memcpy(&v, f.data + i, 4); out.push_back(v); }
+    } else out.push_back(f32_of(f));
+}
+void packed_ints(const Field& f, std::vector<int64_t>& out) {
+    if (f.wt == 2) { Cursor q{f.data, f.data + f.len}; while (!q.done()) out.push_back((int64_t)read_varint(q)); }
+    else out.push_back((int64_t)varint_of(f));
+}
+constexpr uint64_t kMaxElems = 1ull << 32;      // no tensor of a model this engine can run is larger
 
-void parse_tensor(const uint8_t* p, size_t n, OnnxTensor& t) {
-    Cursor c{p, p + n};
+void parse_tensor(const uint8_t* p, size_t len, OnnxTensor& t) {
+    Cursor c{p, p + len};
     Field f;
     while (next_field(c, f)) {
         switch (f.num) {
-            case 1:   // dims (possibly packed)
-                if (f.wt == 2) { Cursor q{f.data, f.data + f.len}; while (!q.done()) t.dims.push_back((int64_t)read_varint(q)); }
-                else t.dims.push_back((int64_t)f.varint);
-                break;
-            case 2: t.data_type = (int)f.varint; break;
-            case 4:   // float_data
-                if (f.wt == 2) { for (size_t i = 0; i + 4 <= f.len; i += 4) { float v; memcpy(&v, f.data + i, 4); t.f32_fallback.push_back(v); } }
-                else t.f32_fallback.push_back(f32_of(f));
-                break;
-            case 7:   // int64_data
-                if (f.wt == 2) { Cursor q{f.data, f.data + f.len}; while (!q.done()) t.i64_fallback.push_back((int64_t)read_varint(q)); }
-                else t.i64_fallback.push_back((int64_t)f.varint);
-                break;
+            case 1: packed_ints(f, t.dims); break;          // dims (possibly packed)
+            case 2: t.data_type = (int)varint_of(f); break;
+            case 4: packed_floats(f, t.f32_fallback); break;   // float_data
+            case 7: packed_ints(f, t.i64_fallback); break;     // int64_data
             case 8: t.name = str(f); break;
-            case 9: t.raw = f.data; t.raw_len = f.len; break;
+            case 9:
+                if (f.wt != 2) throw std::runtime_error("onnx: raw_data has wire type " + std::to_string(f.wt));
+                t.raw = f.data; t.raw_len = f.len;
+                break;
             default: break;
         }
     }
     if (t.data_type != 1 && t.data_type != 7)
         throw std::runtime_error("onnx: initializer '" + t.name + "' has unsupported data_type " + std::to_string(t.data_type));
-    size_t esz = t.data_type == 1 ? 4 : 8;
-    if (t.raw && t.raw_len != t.numel() * esz)
-        throw std::runtime_error("onnx: initializer '" + t.name + "' raw_data size mismatch");
+    // element count: non-negative dims, no overflow, bounded
+    uint64_t n = 1;
+    for (auto d : t.dims) {
+        if (d < 0) throw std::runtime_error("onnx: initializer '" + t.name + "' has a negative dimension");
+        if (d != 0 && n > kMaxElems / (uint64_t)d) throw std::runtime_error("onnx: initializer '" + t.name + "' is too large");
+        n *= (uint64_t)d;
+    }
+    const size_t esz = t.data_type == 1 ? 4 : 8;
+    // exactly one payload of exactly numel elements: every later read of numel() elements is in bounds
+    if (t.raw) {
+        if (t.raw_len != n * esz) throw std::runtime_error("onnx: initializer '" + t.name + "' raw_data size mismatch");
+        if (reinterpret_cast<uintptr_t>(t.raw) % esz) {          // protobuf gives no alignment: move to aligned storage
+            if (t.data_type == 1) { t.f32_fallback.resize(n); memcpy(t.f32_fallback.data(), t.raw, n * esz); }
+            else { t.i64_fallback.resize(n); memcpy(t.i64_fallback.data(), t.raw, n * esz); }
+            t.raw = nullptr;
+            t.raw_len = 0;
+        }
+    } else if ((t.data_type == 1 ? t.f32_fallback.size() : t.i64_fallback.size()) != n) {
+        throw std::runtime_error("onnx: initializer '" + t.name + "' holds " +
+                                 std::to_string(t.data_type == 1 ? t.f32_fallback.size() : t.i64_fallback.size()) +
+                                 " values for " + std::to_string(n) + " elements");
+    }
 }
 
 void parse_attr(const uint8_t* p, size_t n, OnnxAttr& a) {
@@ -102,16 +139,10 @@ void parse_attr(const uint8_t* p, size_t n, OnnxAttr& a) {
         switch (f.num) {
             case 1: a.name = str(f); break;
             case 2: a.f = f32_of(f); break;
-            case 3: a.i = (int64_t)f.varint; break;
+            case 3: a.i = (int64_t)varint_of(f); break;
             case 4: a.s = str(f); break;
-            case 7:
-                if (f.wt == 2) { for (size_t i = 0; i + 4 <= f.len; i += 4) { float v; memcpy(&v, f.data + i, 4); a.floats.push_back(v); } }
-                else a.floats.push_back(f32_of(f));
-                break;
-            case 8:
-                if (f.wt == 2) { Cursor q{f.data, f.data + f.len}; while (!q.done()) a.ints.push_back((int64_t)read_varint(q)); }
-                else a.ints.push_back((int64_t)f.varint);
-                break;
+            case 7: packed_floats(f, a.floats); break;
+            case 8: packed_ints(f, a.ints); break;
             default: break;
         }
     }
@@ -126,7 +157,10 @@ void parse_node(const uint8_t* p, size_t n, OnnxNode& nd) {
             case 2: nd.outputs.push_back(str(f)); break;
             case 3: nd.name = str(f); break;
             case 4: nd.op = str(f); break;
-            case 5: { OnnxAttr a; parse_attr(f.data, f.len, a); nd.attrs.push_back(std::move(a)); break; }
+            case 5: {
+                if (f.wt != 2) throw std::runtime_error("onnx: attribute has wire type " + std::to_string(f.wt));
+                OnnxAttr a; parse_attr(f.data, f.len, a); nd.attrs.push_back(std::move(a)); break;
+            }
             default: break;
         }
     }
@@ -168,6 +202,12 @@ void parse_graph(const uint8_t* p, size_t n, OnnxModel& m) {
     Field f;
     while (next_field(c, f)) {
         switch (f.num) {
+            case 1: case 5: case 11: case 12:
+                if (f.wt != 2) throw std::runtime_error("onnx: graph field " + std::to_string(f.num) + " has wire type " + std::to_string(f.wt));
+                break;
+            default: break;
+        }
+        switch (f.num) {
             case 1: { OnnxNode nd; parse_node(f.data, f.len, nd); m.nodes.push_back(std::move(nd)); break; }
             case 2: m.graph_name = str(f); break;
             case 5: { OnnxTensor t; parse_tensor(f.data, f.len, t); std::string nm = t.name; m.initializers.emplace(nm, std::move(t)); break; }
@@ -182,13 +222,21 @@ void parse_graph(const uint8_t* p, size_t n, OnnxModel& m) {
 
 int64_t OnnxTensor::i64(size_t i) const {
     if (data_type != 7) throw std::runtime_error("onnx: tensor '" + name + "' is not int64");
+    if (i >= numel()) throw std::runtime_error("onnx: index " + std::to_string(i) + " out of range for tensor '" + name + "'");
     if (raw) { int64_t v; memcpy(&v, raw + 8 * i, 8); return v; }
     return i64_fallback.at(i);
 }
 
 float OnnxTensor::f32_at(size_t i) const {
     if (data_type != 1) throw std::runtime_error("onnx: tensor '" + name + "' is not float");
-    return f32()[i];
+    if (i >= numel()) throw std::runtime_error("onnx: index " + std::to_string(i) + " out of range for tensor '" + name + "'");
+    if (raw) { float v; memcpy(&v, raw + 4 * i, 4); return v; }
+    return f32_fallback[i];
+}
+
+const float* OnnxTensor::f32() const {
+    if (data_type != 1) throw std::runtime_error("onnx: tensor '" + name + "' is not float");
+    return raw ? reinterpret_cast<const float*>(raw) : f32_fallback.data();   // raw is 4-byte aligned (parse_tensor)
 }
 
 void parse_onnx(OnnxModel& m) {
@@ -205,7 +253,7 @@ void parse_onnx(OnnxModel& m) {
             int64_t ver = 0;
             while (next_field(c2, f2)) {
                 if (f2.num == 1) domain = str(f2);
-                else if (f2.num == 2) ver = (int64_t)f2.varint;
+                else if (f2.num == 2) ver = (int64_t)varint_of(f2);
             }
             if (domain.empty() || domain == "ai.onnx") m.opset = ver;
         }
@@ -222,9 +270,9 @@ void load_onnx(const std::string& path, OnnxModel& out) {
     FILE* fp = fopen(path.c_str(), "rb");
     if (!fp) throw std::runtime_error("cannot open '" + path + "': " + strerror(errno));
     fseek(fp, 0, SEEK_END);
-    long sz = ftell(fp);
+    long sz = ftell(fp);           // a directory reports LONG_MAX / -1 here
     fseek(fp, 0, SEEK_SET);
-    if (sz <= 0) { fclose(fp); throw std::runtime_error("model file '" + path + "' is empty"); }
+    if (sz <= 0 || (unsigned long)sz > (1ul << 34)) { fclose(fp); throw std::runtime_error("model file '" + path + "' is empty or not a regular file"); }
     out.file.resize((size_t)sz);
     size_t got = fread(out.file.data(), 1, (size_t)sz, fp);
     fclose(fp);

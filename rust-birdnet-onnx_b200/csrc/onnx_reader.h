@@ -26,9 +26,8 @@ struct OnnxTensor {
         for (auto d : dims) n *= (size_t)d;
         return n;
     }
-    const float* f32() const {
-        return raw ? reinterpret_cast<const float*>(raw) : f32_fallback.data();
-    }
+    // numel() contiguous, 4-byte-aligned floats (parse_tensor guarantees exactly numel() values exist)
+    const float* f32() const;
     int64_t i64(size_t i = 0) const;
     float f32_at(size_t i = 0) const;
 };

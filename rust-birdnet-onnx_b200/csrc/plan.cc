@@ -335,12 +335,27 @@ struct Matcher {
         return a.outputs[0];
     }
 
+    // Operand format of the tensor-core path: x = fp16 hi + fp16 lo (tc_common.cuh split8).  It carries ~22 mantissa
+    // bits but only the fp16 RANGE: |x| > 65504 would become inf - inf = NaN downstream.  Weights are checked here, at
+    // load time (the reference reports unusable models through ModelLoad as well); activations are the caller's
+    // business and are flagged at run time (bn_ctx_nonfinite_segments).
+    void check_weight_range(const OnnxTensor& W, const std::string& layer) {
+        const float* w = W.f32();
+        const size_t n = W.numel();
+        for (size_t i = 0; i < n; ++i)
+            if (!(std::fabs(w[i]) <= 65504.0f))
+                fail("layer '" + layer + "': weight " + std::to_string(w[i]) + " is outside the fp16 range (|w| <= 65504) of the hi/lo operand format");
+    }
+
     void match_conv(int n) {
         const OnnxNode& nd = m.nodes[n];
         if (nd.inputs.size() != 3) fail("Conv '" + nd.name + "' must have a bias (BatchNorm folded)");
         const OnnxTensor& W = need_init(nd.inputs[1]);
         const OnnxTensor& Bv = need_init(nd.inputs[2]);
         if (W.dims.size() != 4 || W.dims[2] != W.dims[3]) fail("Conv weights must be [cout,cin/g,k,k]");
+        if (W.dims[0] < 1 || W.dims[0] > (1 << 20) || W.dims[1] < 1 || W.dims[1] > (1 << 20) || W.dims[2] < 1 || W.dims[2] > 15)
+            fail("Conv '" + nd.name + "': weight shape out of range");
+        check_weight_range(W, nd.name);
         PlanOp op;
         op.name = nd.name;
         op.cout = (int)W.dims[0];
@@ -409,6 +424,8 @@ struct Matcher {
         const OnnxTensor& W = need_init(nd.inputs[1]);
         const OnnxTensor& Bv = need_init(nd.inputs[2]);
         if (W.dims.size() != 2) fail("Gemm weight must be 2-D");
+        if (W.dims[0] < 1 || W.dims[0] > (1 << 24) || W.dims[1] < 1 || W.dims[1] > (1 << 24)) fail("Gemm '" + nd.name + "': weight shape out of range");
+        check_weight_range(W, nd.name);
         PlanOp op;
         op.kind = OP_LINEAR;
         op.name = nd.name;
