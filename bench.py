@@ -7,6 +7,9 @@
 
 A step = one pass of the whole hot path over one batch of 256 synthetic 48 kHz segments
 (BASELINE.json configs[1]: create_batch_context(256) + predict_batch_with_context).
+`--config 1|3|4|5` runs the other BASELINE.json configurations with the same line schema
+(1: predict_batch B=32; 3: v3.0 B=512; 4: Perch v2 B=256; 5: 28,800 segments + range filter,
+strong scaling over the ranks).
 
   value : device-timed throughput with the batch already resident in HBM (front-end + CNN + fused
           top-k epilogue + D2H of the results), K steps enqueued back to back, CUDA events on the
@@ -38,10 +41,27 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "birdnet_v2.4_segments_per_sec"
 UNIT = "segments/s"
-BATCH = 256
-FAMILY = "birdnet_v24"
+
+# BASELINE.json configs[0..4] -> --config 1..5.  The driver's default (no flag) is --config 2, the configuration the
+# headline metric is quoted on; the others are run by hand (profiles/r02_bench_cfg*.json) with the same line schema.
+CONFIGS = {
+    1: dict(family="birdnet_v24", batch=32, api="predict_batch", metric="birdnet_v2.4_segments_per_sec",
+            workload="BirdNET v2.4-like (random-init seed 0, build-authored graph) predict_batch batch=32, top_k=5 "
+                     "min_conf=0.1 (BASELINE.json configs[0])"),
+    2: dict(family="birdnet_v24", batch=256, api="ctx", metric="birdnet_v2.4_segments_per_sec",
+            workload="BirdNET v2.4-like (random-init seed 0, build-authored graph) batch=256 via "
+                     "BatchInferenceContext: front-end + CNN + fused top-k epilogue (BASELINE.json configs[1])"),
+    3: dict(family="birdnet_v30", batch=512, api="ctx", metric="birdnet_v3.0_segments_per_sec",
+            workload="BirdNET v3.0-like (32 kHz, 160,000 samples, log-mel, 1024-d embedding + 11,560 logits) batch=512 via "
+                     "BatchInferenceContext (BASELINE.json configs[2])"),
+    4: dict(family="perch_v2", batch=256, api="predict_batch", metric="perch_v2_segments_per_sec",
+            workload="Perch-v2-like (32 kHz, 160,000 samples, log-mel 500x128, 1536-d embedding + 14,795 logits) batch=256 "
+                     "via predict_batch - the reference's context path refuses Perch (BASELINE.json configs[3])"),
+    5: dict(family="birdnet_v24", batch=256, api="ctx", metric="birdnet_v2.4_segments_per_sec", total_segments=28800,
+            workload="24 h of 48 kHz audio = 28,800 BirdNET v2.4 segments, sharded over the GPUs in batches of 256, fused "
+                     "range filter (rerank on) + top_k=5 min_conf=0.1 (BASELINE.json configs[4]); strong scaling"),
+}
 
 
 def _peaks():
@@ -158,17 +178,18 @@ def _dist():
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port timed on the host cores
 # ----------------------------------------------------------------------------------------------
-def _cpu_oracle_rate(n_target_s: float, batch: int, max_segments: int):
+def _cpu_oracle_rate(n_target_s: float, batch: int, max_segments: int, family: str = "birdnet_v24"):
     import torch
-    from birdnet_b200.modelgen import get_spec, synth
+    from birdnet_b200.modelgen import get_spec, synth      # modelgen never maps the product .so (lazy package root)
     from birdnet_b200.modelgen.make_models import ensure_model
     from oracle.model_oracle import ModelOracle, load_initializers
     from oracle import postprocess_oracle as po
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    spec = get_spec(FAMILY)
-    orc = ModelOracle(spec, load_initializers(ensure_model(FAMILY)))
-    audio = synth.batch(0, batch, 144000, 48000)
+    spec = get_spec(family)
+    orc = ModelOracle(spec, load_initializers(ensure_model(family)))
+    fe = spec.frontend
+    audio = synth.batch(0, batch, fe.sample_count, fe.sample_rate)
 
     def step():
         logits, _ = orc.logits_and_embeddings(audio)
@@ -186,27 +207,40 @@ def _cpu_oracle_rate(n_target_s: float, batch: int, max_segments: int):
 
 
 def run_reference(args):
+    """CPU arm: the oracle port of the reference's path (front-end + CNN in torch CPU FP32 + the C restatement of
+    postprocess.rs) on all host cores.  A step is a bounded sample of the workload - one batch of 32 segments, the
+    reference's own CPU-runnable batch (BASELINE.json configs[0]); the metric is a per-segment rate, so the sample size
+    does not change its meaning (the GPU arm's step is 256 segments: stated in `config`).  Timed per step, at least
+    10 s in total, median over steps (round-1 runs of 20 steps spread 309-496 segments/s)."""
     rank, local, world = _dist()
     if rank != 0:
         return 0
-    batch = 32                               # BASELINE.json configs[0]: predict_batch batch=32 on CPU
-    rate, cores, nseg, dt, step = _cpu_oracle_rate(4.0, batch, 64)   # builds the oracle + a short calibration
+    cfg = CONFIGS[args.config]
+    batch = 32
+    rate, cores, nseg, dt, step = _cpu_oracle_rate(2.0, batch, 64, cfg["family"])   # builds the oracle + a short calibration
     for _ in range(max(args.warmup, 0)):
         step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    per_step = []
+    t_all = time.perf_counter()
+    while len(per_step) < args.steps or (time.perf_counter() - t_all) < 10.0:
+        t0 = time.perf_counter()
         step()
-    dt = time.perf_counter() - t0
-    value = args.steps * batch / dt
+        per_step.append(time.perf_counter() - t0)
+        if len(per_step) >= 400:
+            break
+    med = float(np.median(per_step))
+    value = batch / med
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(per_step), "warmup": args.warmup, "ms_per_step": 1e3 * med,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BirdNET v2.4-like (random-init seed 0) batch=256 hot path; this arm: "
-                               "bounded sample, batch 32 per step on the host cores",
-                   "global_batch": batch, "top_k": 5, "min_confidence": 0.1},
+        "config": {"workload": cfg["workload"] + "; this arm: bounded sample, batch 32 per step on the host cores "
+                               "(per-segment rate; the GPU arm's step is %d segments)" % cfg["batch"],
+                   "global_batch": batch, "top_k": 5, "min_confidence": 0.1,
+                   "timing": "median of %d per-step times over %.1f s (min %.0f, max %.0f segments/s)"
+                             % (len(per_step), sum(per_step), batch / max(per_step), batch / min(per_step))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} segments, torch {__import__('torch').__version__} CPU FP32 "
+                         "sample": f"{len(per_step)} steps x {batch} segments, torch {__import__('torch').__version__} CPU FP32 "
                                    "oracle port (ORT CPU cannot run in this image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,6 +252,33 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # this build
 # ----------------------------------------------------------------------------------------------
+def _kernel_class(name: str) -> str:
+    """Stage name -> the kernel (class) that runs it; `kernel_classes` sums every launch of one class."""
+    if name == "normalize":
+        return "front-end: min/max + normalise (k_minmax_partial, k_normalize*)"
+    if name.startswith("spectrogram"):
+        return "front-end: spectrogram GEMM (k_tc_conv / k_fe_spec)"
+    if name == "logmel":
+        return "front-end: log-mel (k_logmel)"
+    if name.startswith("stem"):
+        return "stem conv (k_stem_planes)"
+    if ".mbconv" in name:
+        return "fused MBConv block (k_mbconv)"
+    if ".dw." in name:
+        return "depthwise + squeeze-excite (k_dw_se)"
+    if ".fused." in name:
+        return "3x3 conv (k_tc_conv, halo / gather producers)"
+    if ".expand." in name or ".project" in name or name.startswith("head_conv"):
+        return "1x1 conv (k_tc_conv, TMA producer)"
+    if name.startswith("gap"):
+        return "global pool (k_gap_planes)"
+    if name == "topk_epilogue":
+        return "top-k / sigmoid / range mask (k_topk_small)"
+    if name == "d2h":
+        return "result fetch (D2H)"
+    return "dense head (k_tc_conv)"
+
+
 def _stage_roofline(spec, stage_times, batch, peaks):
     """Per-stage algorithmic work -> achieved rate; returns (dominant stage dict, all stages)."""
     rows = {r["name"]: r for r in spec.layer_table()}
@@ -231,7 +292,20 @@ def _stage_roofline(spec, stage_times, batch, peaks):
         if "_" in base and base.rsplit("_", 1)[1].isdigit() and base.rsplit("_", 1)[0] in rows:
             base = base.rsplit("_", 1)[0]
         d = {"stage": name, "ms": ms, "share": ms / total}
-        if base in rows:
+        if name.endswith(".mbconv"):
+            # fused MBConv block: algorithmic bytes = block input read once + block output written once (+ weights);
+            # the expanded tensors never leave the SM.  FLOPs = expand + depthwise + project.
+            blk = name[:-len(".mbconv")]
+            parts = [rows[k] for k in (blk + ".expand", blk + ".dw", blk + ".project") if k in rows]
+            if len(parts) == 3:
+                byts = 4.0 * ((parts[0]["in_elems"] + parts[2]["out_elems"]) * batch + sum(r["w_elems"] for r in parts))
+                flops = 2.0 * sum(r["macs"] for r in parts) * batch
+                d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                         alg_per_segment=4 * (parts[0]["in_elems"] + parts[2]["out_elems"]),
+                         tensor_tflops=flops / (ms * 1e-3) / 1e12)
+            else:
+                continue
+        elif base in rows:
             # a layer is bound by whichever is slower at peak: its FLOPs on the tensor pipe or its
             # activation + weight bytes through HBM (FP32-equivalent storage: 4 B per element)
             r = rows[base]
@@ -247,17 +321,22 @@ def _stage_roofline(spec, stage_times, batch, peaks):
                          alg_per_segment=4 * (r["in_elems"] + r["out_elems"]),
                          tensor_tflops=flops / (ms * 1e-3) / 1e12)
         elif name.startswith("spectrogram"):
-            s = fe.specs[int(name[-1])]
-            t = s.n_frames(fe.sample_count)
+            idx = int(name[-1]) if name[-1].isdigit() else None
+            specs = fe.specs if idx is None else [fe.specs[idx]]
             # algorithmic bytes: audio read once (shared by both branches: counted half each) + spectrogram written once
-            byts = (fe.sample_count * 4 / len(fe.specs) + s.n_mels * t * 4) * batch
-            d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
-                     alg_per_segment=fe.sample_count * 4 / len(fe.specs) + s.n_mels * t * 4,
-                     tensor_equiv_tflops=2.0 * t * s.n_fft * s.n_mels * batch / (ms * 1e-3) / 1e12)
+            per = sum(fe.sample_count * 4 / len(fe.specs) + sp.n_mels * sp.n_frames(fe.sample_count) * 4 for sp in specs)
+            fl = sum(2.0 * sp.n_frames(fe.sample_count) * sp.n_fft * sp.n_mels for sp in specs)
+            d.update(bound="hbm", achieved=per * batch / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                     alg_per_segment=per, tensor_equiv_tflops=fl * batch / (ms * 1e-3) / 1e12)
+        elif name == "logmel":
+            sp = fe.specs[0]
+            per = fe.sample_count * 4 + fe.n_frames() * sp.n_mels * 4      # audio read once + spectrogram written once
+            d.update(bound="hbm", achieved=per * batch / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s", alg_per_segment=per)
         elif name == "normalize":
-            byts = fe.sample_count * 4 * 2 * batch
+            # min/max pass: the audio is read once (the normalised copy is no longer materialised)
+            byts = fe.sample_count * 4 * batch
             d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
-                     alg_per_segment=fe.sample_count * 8)
+                     alg_per_segment=fe.sample_count * 4)
         elif name == "topk_epilogue":
             byts = (spec.num_species * 4 + 5 * 8) * batch
             d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
@@ -270,12 +349,49 @@ def _stage_roofline(spec, stage_times, batch, peaks):
     return dom, out
 
 
+def _pinned_copy_rates(torch, device, in_bytes, out_bytes, reps=10):
+    """Live staging roofline: pinned cudaMemcpyAsync H2D / D2H rates (GB/s) of batch-sized buffers on this GPU, CUDA
+    events on the copy stream (tools/pcie_bench.cu is the multi-GPU version of the same measurement)."""
+    h_in = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(in_bytes, dtype=torch.uint8, device=device)
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device=device)
+    st = torch.cuda.Stream(device=device)
+    rates = []
+    with torch.cuda.stream(st):
+        for src, dst, n in ((h_in, d_in, in_bytes), (d_out, h_out, out_bytes)):
+            for _ in range(2):
+                dst.copy_(src, non_blocking=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            e1.record(st)
+            e1.synchronize()
+            rates.append(reps * n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return rates[0], rates[1]
+
+
+def _range_mask(n: int, seed: int = 5):
+    """Dense tri-state + scores from a seeded synthetic location-score vector: scores = the
+    reference's mock_embeddings LCG, 30 % of the species absent from the meta model's list, threshold 0.01 for the
+    list (RangeFilter::predict) and 0.03 for the filter so the drop arm fires."""
+    from birdnet_b200.modelgen import synth
+    score = synth.mock_embeddings(n, seed).astype(np.float32)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    present = (rng.random(n) < 0.7) & (score >= np.float32(0.01))
+    state = np.where(~present, 0, np.where(score >= np.float32(0.03), 1, 2)).astype(np.uint8)
+    return state, score
+
+
 def run_ours(args):
     import torch
     import birdnet_b200 as bb
     from birdnet_b200.modelgen import get_spec, synth
     from birdnet_b200.modelgen.make_models import ensure_model, synthetic_labels
 
+    cfg = CONFIGS[args.config]
+    family = cfg["family"]
     rank, local, world = _dist()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this build has no CPU fallback (use --impl reference for the CPU arm)")
@@ -286,17 +402,32 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = _peaks()
-    spec = get_spec(FAMILY)
-    path = ensure_model(FAMILY)
+    spec = get_spec(family)
+    fe = spec.frontend
+    S, SR = fe.sample_count, fe.sample_rate
+    path = ensure_model(family)
     # host gather threads per call: the ranks of one box share its cores
     pack_threads = max(2, ((os.cpu_count() or 2) // max(world, 1)) // 2)
     clf = (bb.Classifier.builder().model_path(path).labels(synthetic_labels(spec.num_species))
            .top_k(5).min_confidence(0.1).device_id(local).pack_threads(pack_threads).build())
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    # each rank owns its own shard of the synthetic stream (weak scaling: 256 segments per rank per step)
-    audio = synth.batch(rank * B, B, 144000, 48000)
+    B = args.batch or cfg["batch"]
+    K, W = args.steps, max(args.warmup, 3)
+    perch = family == "perch_v2"
+    strong = "total_segments" in cfg
+    if strong:
+        state, score = _range_mask(spec.num_species)
+        clf.set_range_filter_dense(state, score, True)
+        # strong scaling: the 28,800 segments are split over the ranks in whole batches (multi_gpu.shard_range)
+        from birdnet_b200.multi_gpu import shard_range
+        lo, hi = shard_range(cfg["total_segments"], rank, world, B)
+        my_batches = [(x, min(hi, x + B)) for x in range(lo, hi, B)]
+        K = len(my_batches)
+    # each rank owns its own shard of the synthetic stream (weak scaling: B segments per rank per step; strong
+    # scaling: the recording is the 256 distinct synthetic segments repeated, the rank's batches rotate through them)
+    audio = synth.batch(rank * B, B, S, SR)
     segs = list(audio)
-    ctx = clf.create_batch_context(B)
+    new_ctx = (lambda: clf.create_batch_context(B, allow_perch=True)) if perch else (lambda: clf.create_batch_context(B))
+    ctx = new_ctx()
 
     def barrier():
         if dist is not None:
@@ -307,7 +438,7 @@ def run_ours(args):
     d_audio = torch.from_numpy(audio).cuda(local)
     lanes = [ctx]
     while len(lanes) < clf.compute_lanes():
-        lanes.append(clf.create_batch_context(B))
+        lanes.append(new_ctx())
     streams = [torch.cuda.ExternalStream(c.stream_ptr(), device=torch.device("cuda", local)) for c in lanes]
     for i in range(W * len(lanes)):
         lanes[i % len(lanes)].enqueue_device(d_audio.data_ptr(), B, True)
@@ -320,8 +451,11 @@ def run_ours(args):
     barrier()
     sampler.start()
     ev0.record(streams[0])
+    n_dev_segments = 0
     for i in range(K):
-        lanes[i % len(lanes)].enqueue_device(d_audio.data_ptr(), B, True)
+        nb = (my_batches[i][1] - my_batches[i][0]) if strong else B      # the last batch of a shard may be ragged
+        lanes[i % len(lanes)].enqueue_device(d_audio.data_ptr(), nb, True)
+        n_dev_segments += nb
     for e, s_ in zip(ev_end, streams):
         e.record(s_)
     for c in lanes:
@@ -335,21 +469,31 @@ def run_ours(args):
         ctx.wait()
     clocks = sampler.stop()
     if dist is not None:
-        t = torch.tensor([dev_ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    value = world * B * K / (dev_ms * 1e-3)
+        t = torch.tensor([dev_ms, float(n_dev_segments)], device=f"cuda:{local}", dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dev_ms, n_all = float(tm[0].item()), float(t[1].item())
+    else:
+        n_all = float(n_dev_segments)
+    value = n_all / (dev_ms * 1e-3)
 
     # ---- e2e: public API with host slices, `depth` contexts driven by `depth` host threads ------
     # headline: the caller keeps its segments in page-locked host memory (bb.pinned_array -> bn_host_alloc), so
     # the engine DMAs them in place; `e2e_pageable`: ordinary numpy memory, gathered into the engine's pinned slab
+    use_ctx = cfg["api"] == "ctx"
     depth = max(1, args.pipeline_depth)
-    ctxs = [ctx] + [clf.create_batch_context(B) for _ in range(depth - 1)]
+    if not use_ctx:
+        depth = min(depth, 4)                               # bn_engine_run: pool of 4 internal contexts
+    ctxs = ([ctx] + [new_ctx() for _ in range(depth - 1)]) if use_ctx else []
     pinned = bb.pinned_array(audio.shape)
     pinned[:] = audio
     segs_pinned = list(pinned)
-    n_e2e = depth * max(16, -(-K // depth))              # whole rounds: every thread drives the same number of batches
     E2E_REPS = 5                                         # median of >= 5 runs
+    if strong:
+        n_e2e = K
+    else:
+        n_e2e = depth * max(16, -(-K // depth))          # whole rounds: every thread drives the same number of batches
     # every call hands back ~1,800 small result objects; with torch's million-object heap loaded, the full garbage
     # collections they trigger each stop all driver threads for ~25 ms (seen in the BN_TRACE_RUN timeline) - park the
     # start-up heap in the permanent generation, as a long-running service would
@@ -359,18 +503,30 @@ def run_ours(args):
 
     run_log = []
 
+    def call(t, seg_list):
+        if use_ctx:
+            return clf.predict_batch_with_context(ctxs[t], seg_list)
+        return clf.predict_batch(seg_list)
+
     def run_e2e(seg_list):
-        for c in ctxs:
+        for t in range(depth):
             for _ in range(2):
-                clf.predict_batch_with_context(c, seg_list)
+                call(t, seg_list)
         sink = [0] * depth
+        done = [0] * depth
 
         def e2e_worker(t):
             for i in range(t, n_e2e, depth):
-                res = clf.predict_batch_with_context(ctxs[t], seg_list)
+                sl = seg_list
+                if strong and (my_batches[i][1] - my_batches[i][0]) != B:
+                    sl = seg_list[: my_batches[i][1] - my_batches[i][0]]
+                res = call(t, sl)
                 sink[t] += len(res[0].predictions) + len(res)
+                done[t] += len(res)
         rates = []
         for _ in range(E2E_REPS):
+            for t in range(depth):
+                done[t] = 0
             barrier()
             t0 = time.perf_counter()
             th = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(depth)]
@@ -378,28 +534,40 @@ def run_ours(args):
             [x.join() for x in th]
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            nseg = float(sum(done))
             if dist is not None:
-                t = torch.tensor([dt], device=f"cuda:{local}")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            rates.append(world * B * n_e2e / dt)
+                tm = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
+                ts = torch.tensor([nseg], device=f"cuda:{local}", dtype=torch.float64)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+                dt, nseg = float(tm.item()), float(ts.item())
+            rates.append(nseg / dt)
         run_log.append([round(r) for r in rates])
         return float(np.median(rates))
 
     e2e_value = run_e2e(segs_pinned)
     e2e_pageable = run_e2e(segs)
-    h2d = B * 144000 * 4
-    d2h = B * spec.num_species * 4 + B * 5 * 8 + B * 4
+    E = spec.embedding_dim or 0
+    h2d = B * S * 4
+    d2h = B * spec.num_species * 4 + B * E * 4 + B * 5 * 8 + B * 4
+
+    # single-call latency of the API at this batch (one thread, nothing else in flight)
+    lat = []
+    for _ in range(7):
+        t0 = time.perf_counter()
+        call(0, segs_pinned)
+        lat.append(1e3 * (time.perf_counter() - t0))
+    call_latency_ms = float(np.median(lat))
 
     # ---- extra: the same metric through the on-device ingest path: the recording is
     # handed over as 16-bit PCM and read_wav's conversion + chunk_audio run on the GPU (bn_ctx_run_pcm16) ----
     ingest = None
-    if not args.no_ingest:
+    if not args.no_ingest and use_ctx and not strong:
         n_b = 8                                                   # batches per recording
-        pcm = bb.pinned_array((n_b * B * 144000,), np.int16)      # the recording sits in page-locked host memory
+        pcm = bb.pinned_array((n_b * B * S,), np.int16)           # the recording sits in page-locked host memory
         pcm[:] = np.tile((np.clip(audio.reshape(-1), -1.0, 1.0) * 32767.0).astype(np.int16), n_b)
         for c in ctxs:
-            clf.predict_pcm16_stream(c, pcm[: B * 144000])
+            clf.predict_pcm16_stream(c, pcm[: B * S])
         got = [0] * depth
 
         def pcm_worker(t):
@@ -418,12 +586,12 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 pcm_s = float(t.item())
             pcm_rates.append(world * sum(got) / pcm_s)
-        ingest = {"value": float(np.median(pcm_rates)), "unit": UNIT, "h2d_bytes_per_step": B * 144000 * 2,
+        ingest = {"value": float(np.median(pcm_rates)), "unit": UNIT, "h2d_bytes_per_step": B * S * 2,
                   "segments": world * sum(got), "api": "Classifier.predict_pcm16_stream -> bn_ctx_run_pcm16 "
                   "(16-bit PCM in, conversion + chunking on the device; not the reference's f32-slice API)"}
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the engine's stream ----
-    roof, stages = None, []
+    roof, stages, classes = None, [], []
     if rank == 0:
         ctx.set_profiling(True)
         acc = {}
@@ -435,6 +603,22 @@ def run_ours(args):
         ctx.set_profiling(False)
         st = [(n, float(np.mean(v))) for n, v in acc.items()]
         dom, stages = _stage_roofline(spec, st, B, peaks)
+        tot_ms = sum(ms for _, ms in st) or 1.0
+        by_class = {}
+        for n, ms in st:
+            c = by_class.setdefault(_kernel_class(n), {"ms": 0.0, "stages": 0})
+            c["ms"] += ms
+            c["stages"] += 1
+        classes = [{"class": k, "ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4), "stages": v["stages"]}
+                   for k, v in sorted(by_class.items(), key=lambda kv: -kv[1]["ms"])]
+        # staging over PCIe: what the end-to-end API moved per second against the pinned-copy rate measured live
+        h2d_gbs, d2h_gbs = _pinned_copy_rates(torch, torch.device("cuda", local), h2d, max(d2h, 1 << 20))
+        moved = e2e_value / max(world, 1) * (h2d + d2h) / B / 1e9          # GB/s through this GPU's link
+        stages.append({"stage": "staging (H2D of the segments + D2H of the results, per GPU)", "bound": "pcie",
+                       "achieved": moved, "peak": h2d_gbs, "unit": "GB/s", "frac": moved / h2d_gbs,
+                       "alg_per_segment": (h2d + d2h) / B, "ms": 1e3 * (h2d / (h2d_gbs * 1e9) + d2h / (d2h_gbs * 1e9)),
+                       "share": None, "peak_source": "pinned cudaMemcpyAsync H2D measured in this run (%.1f GB/s; D2H %.1f GB/s)"
+                                                     % (h2d_gbs, d2h_gbs)})
         if dom:
             traffic, traffic_src = _ncu_traffic()
             roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
@@ -442,38 +626,43 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": (dom["alg_per_segment"] * B if dom["bound"] == "hbm" else None),
                     "kernel": dom["stage"], "kernel_ms": dom["ms"],
                     "share_of_step": dom["share"], "peak_source": peaks["src"] + (" sustained" if dom["bound"] == "tensor" else ""),
-                    "algorithmic_per_segment": dom["alg_per_segment"]}
+                    "algorithmic_per_segment": dom["alg_per_segment"],
+                    "dominant_class": classes[0] if classes else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, nseg, dt, _ = _cpu_oracle_rate(12.0, 8, 4096)
+        rate, cores, nseg, dt, _ = _cpu_oracle_rate(12.0, 8, 4096, family)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nseg} segments in batches of 8 ({dt:.1f} s), torch CPU FP32 oracle port; ORT CPU cannot run in this image"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BirdNET v2.4-like (random-init seed 0, build-authored graph) batch=256 via "
-                                   "BatchInferenceContext: front-end + CNN + fused top-k epilogue (BASELINE.json configs[1])",
-                       "global_batch": B * world, "segment_samples": 144000, "top_k": 5, "min_confidence": 0.1,
-                       "l2_policy": "inputs larger than L2 (147 MB batch > 126 MB L2)",
+            "config": {"workload": cfg["workload"], "bench_config": args.config,
+                       "global_batch": B * world, "segment_samples": S, "top_k": 5, "min_confidence": 0.1,
+                       "total_segments": cfg.get("total_segments"),
+                       "l2_policy": "inputs larger than L2 (%d MB batch > 126 MB L2)" % (B * S * 4 // 1000000) if B * S * 4 > 126e6
+                                    else "batch of %d MB fits L2; 2 compute lanes alternate two contexts' buffers" % (B * S * 4 // 1000000),
                        "compute_lanes": len(lanes), "numa_node": numa_node,
                        "parallelism": f"{world} independent per-GPU shards, no collective",
                        "precision_policy": "FP32-equivalent (see DESIGN.md)",
+                       "api": "predict_batch_with_context" if use_ctx else "predict_batch",
+                       "call_latency_ms": call_latency_ms,
                        "e2e_pipeline_depth": depth, "e2e_runs": "median of 5 runs of %d batches" % n_e2e, "e2e_run_values": run_log, "host_gc": "gc.freeze() after start-up", "host_cores": os.cpu_count(), "host_pack_threads_per_call": pack_threads},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "inputs": "256 host slices per step in page-locked host memory (bn_host_alloc), copied to the GPU in place"},
+                    "inputs": "%d host slices per step in page-locked host memory (bn_host_alloc), copied to the GPU in place" % B},
             "e2e_pageable": {"value": e2e_pageable, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                             "inputs": "256 pageable host slices per step, gathered into the engine's pinned slab first"},
+                             "inputs": "%d pageable host slices per step (the true drop-in case), gathered into the engine's pinned slab first" % B},
             "ingest_pcm16": ingest,
             "gpu_launches": int(launches_per_step * K),
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "kernel_classes": classes,
             "stages": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in s.items()} for s in
-                       sorted(stages, key=lambda x: -x["ms"])[:12]],
+                       sorted(stages, key=lambda x: -(x["ms"] or 0))[:14]],
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -488,7 +677,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[n-1]; default 2 = the headline")
+    ap.add_argument("--batch", type=int, default=0, help="override the configuration's batch size")
     ap.add_argument("--pipeline-depth", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ingest", action="store_true")

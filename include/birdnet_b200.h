@@ -203,14 +203,20 @@ int bn_topk_apply(bn_engine* engine, const float* logits, uint64_t rows, uint64_
                   int32_t has_min_confidence, float min_confidence, const uint8_t* state, const float* score,
                   int32_t rerank, bn_pred* out, uint32_t* out_count);
 
-/* ---- multi-GPU: contiguous block partition, no collective ------ */
+/* ---- multi-GPU: shared batch queue, no collective --------------
+ * Per device one engine replica and `depth` contexts (each with its own host thread inside bn_pool_run); all of them
+ * pull whole batches of ctx_batch segments from one queue, so H2D, kernels and D2H of consecutive batches overlap on
+ * every device.  bn_pool_create = depth 3 (or BN_POOL_DEPTH).  A device id may be listed more than once. */
 int bn_pool_create(const char* onnx_path, const int32_t* device_ids, int32_t n_devices, int32_t model_type_override,
                    uint64_t ctx_batch, bn_pool** out);
+int bn_pool_create_ex(const char* onnx_path, const int32_t* device_ids, int32_t n_devices, int32_t model_type_override,
+                      uint64_t ctx_batch, int32_t depth, bn_pool** out);
 void bn_pool_destroy(bn_pool* pool);
 int bn_pool_set_postprocess(bn_pool* pool, uint64_t top_k, int32_t has_min_confidence, float min_confidence);
 int bn_pool_set_range_filter(bn_pool* pool, const uint8_t* state, const float* score, uint64_t n, int32_t rerank);
 /* Runs all segments; results are gathered in caller order into caller-provided host arrays:
- * logits [n_segments][num_species], embeddings (or NULL), topk [n_segments][topk_stride]. */
+ * logits [n_segments][num_species] (or NULL), embeddings (or NULL), topk [n_segments][topk_stride].
+ * opts (timeout / cancellation, src/inference_options.rs) applies to every batch of the call. */
 int bn_pool_run(bn_pool* pool, const float* const* seg_ptrs, const uint64_t* seg_lens, uint64_t n_segments,
                 const bn_run_opts* opts, float* logits, float* embeddings, bn_pred* topk, uint32_t* topk_count,
                 uint64_t topk_stride);

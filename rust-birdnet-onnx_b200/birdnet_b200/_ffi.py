@@ -107,6 +107,7 @@ SIGNATURES = {
                                 C.c_float, _P(C.c_uint8), _P(C.c_float), C.c_int32, _P(Pred),
                                 _P(C.c_uint32)]),
     "bn_pool_create": (C.c_int, [C.c_char_p, _P(C.c_int32), C.c_int32, C.c_int32, C.c_uint64, _P(_vp)]),
+    "bn_pool_create_ex": (C.c_int, [C.c_char_p, _P(C.c_int32), C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _P(_vp)]),
     "bn_pool_destroy": (None, [_vp]),
     "bn_pool_set_postprocess": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.c_float]),
     "bn_pool_set_range_filter": (C.c_int, [_vp, _P(C.c_uint8), _P(C.c_float), C.c_uint64, C.c_int32]),

@@ -320,6 +320,14 @@ class Classifier:
             self._h, state.ctypes.data_as(C.POINTER(C.c_uint8)),
             score.ctypes.data_as(C.POINTER(C.c_float)), len(state), 1 if rerank else 0))
 
+    def set_range_filter_dense(self, state: np.ndarray, score: np.ndarray, rerank: bool) -> None:
+        """Same, from the dense form directly: state[i] in {0 absent -> keep, 1 keep (x score when rerank), 2 drop}."""
+        state = np.ascontiguousarray(state, dtype=np.uint8)
+        score = np.ascontiguousarray(score, dtype=np.float32)
+        raise_for_status(_lib.bn_engine_set_range_filter(
+            self._h, state.ctypes.data_as(C.POINTER(C.c_uint8)),
+            score.ctypes.data_as(C.POINTER(C.c_float)), len(state), 1 if rerank else 0))
+
     def compute_lanes(self) -> int:
         """Number of compute lanes of the engine (contexts are assigned to them in turn)."""
         return int(_lib.bn_engine_compute_lanes(self._h))

@@ -97,6 +97,27 @@ def test_epilogue_bit_exact_on_lcg_logits(n, k, mc):
             assert idx[r, :c].tolist() == ridx[r, :c].tolist()
 
 
+@pytest.mark.parametrize("n,k", [(14795, 14795), (14795, 2 ** 64 - 1), (40000, 50), (70001, 70001)])
+def test_epilogue_has_no_size_limit(n, k):
+    """postprocess.rs:50 clamps k to n and accepts any n; sorts that do not fit shared memory run from a
+    global workspace (k > ~11.7k on Perch used to be cudaErrorInvalidValue)."""
+    from oracle import postprocess_oracle as po
+    rows = 3
+    lg = np.stack([po.random_logits(n, 4000 + s) for s in range(rows)])
+    lg = (lg + np.arange(n, dtype=np.float32)[None, :] * np.float32(1e-7)).astype(np.float32)
+    idx, conf, cnt = _gpu_topk(lg, k, 0.25)
+    ridx, rconf, rcnt = po.top_k_batch(lg, k, 0.25)
+    assert np.array_equal(cnt, rcnt)
+    for r in range(rows):
+        c = cnt[r]
+        assert np.abs(conf[r, :c] - rconf[r, :c]).max(initial=0) <= 2e-7
+        strict = np.nonzero(np.diff(rconf[r, :c]) < 0)[0]
+        if len(strict) == c - 1:
+            assert idx[r, :c].tolist() == ridx[r, :c].tolist()
+        else:
+            assert sorted(idx[r, :c].tolist()) == sorted(ridx[r, :c].tolist())
+
+
 def test_epilogue_range_mask_and_rerank():
     from oracle import postprocess_oracle as po
     n, rows, k = 6522, 16, 10
@@ -439,3 +460,51 @@ def test_pinned_segments_skip_the_gather_and_match(clf):
     got_m = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, mixed)])
     assert np.array_equal(got_m, ref)
     assert np.array_equal(np.stack([r.raw_scores for r in clf.predict_batch(list(pinned[:5]))]), ref[:5])
+
+
+def test_predict_batch_of_any_size_runs_in_chunks(clf):
+    """bn_engine_run: 300 segments = one chunk of 256 + one of 44 on a pooled internal context; the result must be
+    what the batch-context path gives for the same segments (classifier.rs:676-727 takes any batch)."""
+    audio = synth.batch(0, 10, 144000, 48000)
+    segs = [audio[i % 10] for i in range(300)]
+    res = clf.predict_batch(segs)
+    assert len(res) == 300
+    ctx = clf.create_batch_context(16)
+    ref = clf.predict_batch_with_context(ctx, [audio[i] for i in range(10)])
+    for i, r in enumerate(res):
+        q = ref[i % 10]
+        assert [p.index for p in r.predictions] == [p.index for p in q.predictions]
+        assert np.array_equal(r.raw_scores, q.raw_scores), i
+    # many short-lived threads: the internal pool stays bounded (4 contexts), calls queue instead of allocating
+    out = [None] * 12
+
+    def work(t):
+        out[t] = clf.predict_batch([audio[t % 10]] * 3)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(12)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for t in range(12):
+        assert np.array_equal(out[t][0].raw_scores, ref[t % 10].raw_scores)
+
+
+def test_activation_overflow_is_reported(v24_spec, v24_model_path, tmp_path):
+    """hi/lo fp16 operands carry the fp16 RANGE: a model whose activations leave it yields NaN logits; the run is
+    Ok (as a NaN would be in the reference) and bn_ctx_nonfinite_segments says how many segments were hit."""
+    from birdnet_b200.modelgen import make_weights, write_model
+    w = make_weights(v24_spec)
+    for name in ("stem.weight", "s1b0.fused.weight", "s2b0.fused.weight"):
+        w[name] = (w[name] * np.float32(2.0e3)).astype(np.float32)       # weights stay far below 65504
+    path = os.path.join(str(tmp_path), "hot.onnx")
+    write_model(v24_spec, path, w)
+    c = (bb.Classifier.builder().model_path(path).labels(synthetic_labels(v24_spec.num_species)).top_k(5).build())
+    ctx = c.create_batch_context(4)
+    audio = synth.batch(0, 4, 144000, 48000)
+    res = c.predict_batch_with_context(ctx, list(audio))
+    assert len(res) == 4
+    bad = sum(int(not np.isfinite(r.raw_scores).all()) for r in res)
+    assert bad >= 1 and ctx.nonfinite_segments() == bad
+    ok = (bb.Classifier.builder().model_path(v24_model_path)
+          .labels(synthetic_labels(v24_spec.num_species)).build())
+    ctx2 = ok.create_batch_context(4)
+    ok.predict_batch_with_context(ctx2, list(audio))
+    assert ctx2.nonfinite_segments() == 0
