@@ -64,7 +64,11 @@ class FrontEnd:
     specs: List[MelSpec]
     # logmel only: y = log_scale * ln(mel(|STFT|) + log_floor), layout [frames, mels]
     pad_end: int = 0           # zeros appended so the frame count is exact
-    log_floor: float = 1e-5
+    # 1e-2 against mel magnitudes that reach ~250 for a full-scale tone (88 dB of range): with 1e-5 the FP32 FFT
+    # noise floor sat ABOVE the log floor and ln() amplified it - the FP32 and FP64 oracles then differed by 0.24 in
+    # the logits of the chirp segment; with 1e-2 they agree to 7e-5 on all ten synthetic kinds (build-authored
+    # constant: the reference fixes none)
+    log_floor: float = 1e-2
     log_scale: float = 0.1
 
     def n_frames(self) -> int:
@@ -265,7 +269,7 @@ def birdnet_v30_spec(seed: int = 0, num_species: int = 11560) -> GraphSpec:
     """32 kHz, 5 s, log-mel front-end (north star), 1024-d embedding + logits."""
     fe = FrontEnd(kind="logmel", sample_rate=32000, sample_count=160000,
                   specs=[MelSpec(1024, 320, 40.0, 15000.0, 128)],
-                  pad_end=0, log_floor=1e-5, log_scale=0.1)
+                  pad_end=0, log_floor=1e-2, log_scale=0.1)
     b = _B()
     x = b.conv("stem", "spec", 1, 32, 3, 2, act="silu")
     x = _backbone(b, x, 32, _V24_STAGES, 1024)
@@ -300,7 +304,7 @@ def perch_v2_spec(seed: int = 0, num_species: int = 14795) -> GraphSpec:
     """
     fe = FrontEnd(kind="logmel", sample_rate=32000, sample_count=160000,
                   specs=[MelSpec(640, 320, 60.0, 16000.0, 128)],
-                  pad_end=320, log_floor=1e-5, log_scale=0.1)
+                  pad_end=320, log_floor=1e-2, log_scale=0.1)
     b = _B()
     x = b.conv("stem", "spec", 1, 32, 3, 2, act="silu")
     x = _backbone(b, x, 32, _PERCH_STAGES, 1536)

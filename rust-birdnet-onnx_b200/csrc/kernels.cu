@@ -1149,10 +1149,14 @@ cudaError_t launch_gap(const float* in, float* out, int batch, int hw, int c, cu
 // Epilogue: top-k by IEEE total order -> sigmoid -> min_confidence -> range mask / rerank
 // (reference: src/postprocess.rs:40-93, src/rangefilter.rs:333-386)
 // ======================================================================================
-__device__ __forceinline__ uint32_t total_order_key(float x) {   // f32::total_cmp as unsigned order
-    uint32_t u = __float_as_uint(x);
+__device__ __forceinline__ uint32_t total_order_key_bits(uint32_t u) {   // f32::total_cmp as unsigned order
+    // opaque to the optimiser: seen as float bits, `u | sign` is rewritten into FADD -|x|, which canonicalises a NaN
+    // (payload and ordering lost; caught by the +NaN known-answer test of postprocess.rs:233-242)
+    asm("" : "+r"(u));
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ uint32_t total_order_key(float x) { return total_order_key_bits(__float_as_uint(x)); }
+__device__ __forceinline__ bool bits_nonfinite(uint32_t u) { return (u & 0x7f800000u) == 0x7f800000u; }
 __device__ __forceinline__ float from_total_order_key(uint32_t k) {
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
     return __uint_as_float(u);
@@ -1274,9 +1278,9 @@ __global__ void __launch_bounds__(1024) k_topk(TopkParams p, int P, unsigned cha
     }
     int bad = 0;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const float x = i < p.n ? lg[i] : 0.f;
-        bad |= !isfinite(x);
-        s_keys[i] = i < p.n ? (((unsigned long long)total_order_key(x) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+        const uint32_t u = i < p.n ? __ldg(reinterpret_cast<const uint32_t*>(lg) + i) : 0u;     // bits, never a float value
+        bad |= bits_nonfinite(u);
+        s_keys[i] = i < p.n ? (((unsigned long long)total_order_key_bits(u) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
     }
     if (p.nonfinite) {
         bad = __syncthreads_or(bad);
@@ -1330,9 +1334,9 @@ __global__ void __launch_bounds__(1024) k_topk_small(TopkParams p) {
 #pragma unroll
     for (int j = 0; j < TOPK_SMALL_EPT; ++j) {
         const int i = tid + j * blockDim.x;
-        const float x = i < p.n ? lg[i] : 0.f;
-        bad |= !isfinite(x);
-        keys[j] = i < p.n ? (((unsigned long long)total_order_key(x) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+        const uint32_t u = i < p.n ? __ldg(reinterpret_cast<const uint32_t*>(lg) + i) : 0u;     // bits, never a float value
+        bad |= bits_nonfinite(u);
+        keys[j] = i < p.n ? (((unsigned long long)total_order_key_bits(u) << 32) | (0xFFFFFFFFu - (uint32_t)i)) : 0ull;
     }
     if (p.nonfinite) {            // a segment whose logits are not all finite: bn_ctx_nonfinite_segments()
         bad = __syncthreads_or(bad);

@@ -36,27 +36,22 @@ def _sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x.astype(np.float64)))
 
 
-def _check(results, ref_logits, ref_emb, model_type, ref64_logits, ref64_emb, k=5, mc=0.1):
-    """Tolerances: the north-star bounds PLUS twice the oracle's own FP32-vs-FP64 distance on that
-    segment.  ln(mel + 1e-5) is ill-conditioned where the FFT noise floor meets the log floor (the
-    chirp segment: torch FP32 and FP64 differ by 0.24 in the v3.0 logits), so there the FP32
-    oracle is itself only known to that distance; everywhere else the extra term is ~1e-5.
-    Logits additionally get a 3e-4 relative term (|logit| reaches 28 where sigmoid saturates)."""
+def _check(results, ref_logits, ref_emb, model_type, k=5, mc=0.1):
+    """North-star tolerances on EVERY segment of every synthetic kind, no per-segment allowance: embeddings and
+    confidences within max-abs 1e-3, raw logits within 5e-3 (+3e-4 relative: |logit| reaches 28 where sigmoid
+    saturates), top-k lists identical wherever the oracle's scores are separated by more than the tolerance.
+    (The log floor of the build-authored log-mel front-ends is 1e-2, which keeps ln() well-conditioned: the FP32
+    and FP64 oracles agree to 7e-5 in the logits on all ten kinds - graphspec.FrontEnd.log_floor.)"""
     from oracle import postprocess_oracle as po
     got = np.stack([r.raw_scores for r in results])
     emb = np.stack([r.embeddings for r in results])
-    noise_l = np.abs(ref_logits - ref64_logits).max(axis=1)
-    noise_e = np.abs(ref_emb - ref64_emb).max(axis=1)
-    noise_c = np.abs(_sigmoid(ref_logits) - _sigmoid(ref64_logits)).max(axis=1)
     for i in range(len(results)):
-        tol = LOGIT_TOL + 3e-4 * np.abs(ref_logits[i]).max() + 2 * noise_l[i]
+        tol = LOGIT_TOL + 3e-4 * np.abs(ref_logits[i]).max()
         assert np.abs(got[i] - ref_logits[i]).max() < tol, (i, np.abs(got[i] - ref_logits[i]).max(), tol)
-        assert np.abs(emb[i] - ref_emb[i]).max() < EMB_TOL + 2 * noise_e[i], i
-        assert np.abs(_sigmoid(got[i]) - _sigmoid(ref_logits[i])).max() < CONF_TOL + 2 * noise_c[i], i
+        assert np.abs(emb[i] - ref_emb[i]).max() < EMB_TOL, (i, np.abs(emb[i] - ref_emb[i]).max())
+        assert np.abs(_sigmoid(got[i]) - _sigmoid(ref_logits[i])).max() < CONF_TOL, i
     worst = 0.0
     for i, r in enumerate(results):
-        if noise_l[i] > LOGIT_TOL:
-            continue                                     # oracle not pinned on this segment (see above)
         assert r.model_type is model_type
         ref = po.top_k_predictions(ref_logits[i], k, mc)
         srt = np.sort(ref_logits[i])[::-1]
@@ -93,30 +88,25 @@ def test_v30_matches_oracle_and_golden(v30):
     assert (cfg.sample_rate, cfg.sample_count, cfg.embedding_dim, cfg.num_species) == (32000, 160000, 1024, 11560)
     audio = synth.batch(0, 10, 160000, 32000)             # one segment of every synthetic kind
     orc = _oracle(spec, path)
-    import torch
     ref_logits, ref_emb = orc.logits_and_embeddings(audio)
-    r64_logits, r64_emb = _oracle(spec, path, torch.float64).logits_and_embeddings(audio)
     res = clf.predict_batch(list(audio))                   # classifier.rs:676-727
-    _check(res, ref_logits, ref_emb, bb.ModelType.BirdNetV30, r64_logits, r64_emb)
+    _check(res, ref_logits, ref_emb, bb.ModelType.BirdNetV30)
     ctx = clf.create_batch_context(10)                     # batch_context.rs:252-262 (output_0 / output_1)
     res2 = clf.predict_batch_with_context(ctx, list(audio))
     for a, b in zip(res, res2):
         assert np.array_equal(a.raw_scores, b.raw_scores) and np.array_equal(a.embeddings, b.embeddings)
     # log-mel front-end alone: [frames][mels], ln() of FP32 FFT magnitudes on both sides
-    ref_spec = orc.forward(audio, keep=["spec"])["spec"].reshape(10, -1)
+    import torch
     ref64_spec = _oracle(spec, path, torch.float64).forward(audio, keep=["spec"])["spec"].reshape(10, -1)
     spec_gpu = ctx.read_tensor("spec", 10)
-    for i in range(10):                                    # per segment: within the FP32 oracle's own noise
-        d = np.abs(spec_gpu[i] - ref_spec[i])
-        n = np.abs(ref_spec[i] - ref64_spec[i])
-        assert d.max() < 1e-4 + 2 * n.max(), (i, d.max(), n.max())
-        assert d.mean() < 1e-5 + 2 * n.mean(), (i, d.mean(), n.mean())
+    for i in range(10):                                    # against the FP64 oracle, every segment, values in [-0.46, 0.61]
+        d = np.abs(spec_gpu[i] - ref64_spec[i])
+        assert d.max() < 1e-3 and d.mean() < 2e-5, (i, d.max(), d.mean())
     g = np.load(os.path.join(GOLD_DIR, "v30_seed0.npz"))
     got = np.stack([r.raw_scores for r in res])
     emb = np.stack([r.embeddings for r in res])
-    pinned = [i for i in range(10) if i != 4]             # the chirp segment is ill-conditioned (see _check)
-    assert np.abs(got[pinned, ::32] - g["logits_every_32"][pinned]).max() < 2 * LOGIT_TOL
-    assert np.abs(emb[pinned][:, ::8] - g["emb_every_8"][pinned]).max() < EMB_TOL
+    assert np.abs(got[:, ::32] - g["logits_every_32"]).max() < 2 * LOGIT_TOL         # all ten segments
+    assert np.abs(emb[:, ::8] - g["emb_every_8"]).max() < EMB_TOL
     one = clf.predict(audio[4])                            # batch-size invariance, bit for bit
     assert np.array_equal(one.raw_scores, got[4]) and np.array_equal(one.embeddings, emb[4])
 
@@ -126,15 +116,12 @@ def test_perch_matches_oracle_and_golden(perch):
     cfg = clf.config()
     assert (cfg.sample_count, cfg.embedding_dim, cfg.num_species) == (160000, 1536, 14795)   # detection.rs:214-232
     audio = synth.batch(0, 10, 160000, 32000)
-    import torch
     ref_logits, ref_emb = _oracle(spec, path).logits_and_embeddings(audio)
-    r64_logits, r64_emb = _oracle(spec, path, torch.float64).logits_and_embeddings(audio)
     res = clf.predict_batch(list(audio))
-    _check(res, ref_logits, ref_emb, bb.ModelType.PerchV2, r64_logits, r64_emb)
+    _check(res, ref_logits, ref_emb, bb.ModelType.PerchV2)
     g = np.load(os.path.join(GOLD_DIR, "perch_seed0.npz"))
     got = np.stack([r.raw_scores for r in res])
-    pinned = [i for i in range(10) if i != 4]
-    assert np.abs(got[pinned, ::32] - g["logits_every_32"][pinned]).max() < 2 * LOGIT_TOL
+    assert np.abs(got[:, ::32] - g["logits_every_32"]).max() < 2 * LOGIT_TOL          # all ten segments
     with pytest.raises(bb.Inference) as e:                 # batch_context.rs:107-114
         clf.create_batch_context(4)
     assert str(e.value) == ("inference failed: BatchInferenceContext does not yet support PerchV2 models. "
@@ -151,7 +138,8 @@ def test_perch_matches_oracle_and_golden(perch):
     spat = ctx.read_tensor("spatial_embedding", 10)
     assert spat.shape == (10, 16 * 4 * 1536)
     ref_spat = np.asarray(keep["spatial_embedding"]).reshape(10, -1)
-    assert np.abs(spat[pinned] - ref_spat[pinned]).max() < 2e-3 * max(1.0, float(np.abs(ref_spat[pinned]).max()))   # un-pooled activations
+    # un-pooled activations of the last conv: |x| reaches ~40, same 1e-3 absolute bound + 1e-4 relative
+    assert np.abs(spat - ref_spat).max() < 1e-3 + 1e-4 * float(np.abs(ref_spat).max()), np.abs(spat - ref_spat).max()
     assert ctx.read_tensor("spectrogram", 10).shape == (10, 500 * 128)
     with pytest.raises(bb.InputSize) as e:
         clf.predict(np.zeros(144000, dtype=np.float32))
