@@ -136,6 +136,31 @@ static void build_real_mel_basis(const SpecBranch& br, std::vector<float>& basis
     }
 }
 
+// MBConv block with squeeze-excite starting at op i (the 1x1 expand conv)?  ops i..i+5 = expand, depthwise, pool, FC silu,
+// FC sigmoid, gated 1x1 projection; the expanded tensor and the depthwise output have no other reader.
+static bool match_mbconv(const Plan& p, size_t i) {
+    if (i + 5 >= p.ops.size()) return false;
+    const PlanOp &ex = p.ops[i], &dw = p.ops[i + 1], &gp = p.ops[i + 2], &f1 = p.ops[i + 3], &f2 = p.ops[i + 4], &pr = p.ops[i + 5];
+    if (ex.kind != OP_CONV || ex.k != 1 || ex.stride != 1 || ex.pad != 0 || ex.act != ACT_SILU || ex.in_scale >= 0 || ex.residual >= 0) return false;
+    if (dw.kind != OP_DWCONV || dw.in != ex.out || dw.act != ACT_SILU || dw.pad != dw.k / 2 || dw.cout != ex.cout) return false;
+    if (gp.kind != OP_GAP || gp.in != dw.out) return false;
+    if (f1.kind != OP_LINEAR || f1.act != ACT_SILU || f1.in != gp.out || f1.cin != dw.cout || f1.in_scale >= 0 || f1.residual >= 0) return false;
+    if (f2.kind != OP_LINEAR || f2.act != ACT_SIGMOID || f2.in != f1.out || f2.cout != dw.cout || f2.in_scale >= 0 || f2.residual >= 0) return false;
+    if (pr.kind != OP_CONV || pr.k != 1 || pr.stride != 1 || pr.pad != 0 || pr.act != ACT_NONE || pr.in != dw.out || pr.in_scale != f2.out) return false;
+    if (pr.residual >= 0 && (pr.residual != ex.in || pr.cout != ex.cin)) return false;
+    // E, D, the pooled vector, the FC outputs: read by nothing else and not model outputs
+    const int inner[5] = {ex.out, dw.out, gp.out, f1.out, f2.out};
+    for (size_t q = 0; q < p.ops.size(); ++q) {
+        if (q >= i && q <= i + 5) continue;
+        for (int t : inner)
+            if (p.ops[q].in == t || p.ops[q].residual == t || p.ops[q].in_scale == t) return false;
+    }
+    for (auto& o : p.outputs)
+        for (int t : inner)
+            if (p.root(o.tensor) == p.root(t)) return false;
+    return mbconv_supported(dw.hin, dw.win, dw.k, dw.stride, ex.cin, ex.cout, pr.cout, f1.cout);
+}
+
 // UMMA N tile for a layer: the largest multiple of 16 (<= 128) that divides cout rounded up to 16
 static int choose_nt(int cout) {
     const int c16 = (cout + 15) / 16 * 16;
@@ -174,6 +199,7 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
     BN_CUDA(init_kernels_for_device());
     BN_CUDA(tc_conv_init_device());
     BN_CUDA(dw_se_init_device());
+    BN_CUDA(mbconv_init_device());
     const char* env_tc = getenv("BN_DISABLE_TC");
     const bool tc_enabled = !(env_tc && env_tc[0] == '1');
     e->tc_mode = tc_enabled;
@@ -226,6 +252,23 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
             BN_CUDA(cudaMalloc(&d.wpack, pack.size() * sizeof(uint16_t)));
             BN_CUDA(cudaMemcpy(d.wpack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
             d.use_tc = true;
+        }
+        // fused MBConv block: expand weights packed per channel group, projection weights output-channel major
+        static const bool no_mbconv = [] { const char* ev = getenv("BN_DISABLE_MBCONV"); return ev && ev[0] == '1'; }();
+        if (tc_enabled && !no_mbconv && e->dev_ops[i].use_tc && match_mbconv(p, i)) {
+            DevOp& d = e->dev_ops[i];
+            const PlanOp &dw = p.ops[i + 1], &pr = p.ops[i + 5];
+            d.mb_group = mbconv_group(dw.hin, dw.win, dw.k);
+            std::vector<uint16_t> pack;
+            int nt_ = 0, kc_ = 0;
+            tc_pack_weights(op.weight.data(), op.cin, op.cout, op.ldw, d.mb_group, pack, &nt_, &kc_);
+            BN_CUDA(cudaMalloc(&d.mb_we_pack, pack.size() * sizeof(uint16_t)));
+            BN_CUDA(cudaMemcpy(d.mb_we_pack, pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            std::vector<float> wt((size_t)pr.cout * pr.cin);
+            for (int c = 0; c < pr.cin; ++c)
+                for (int n = 0; n < pr.cout; ++n) wt[(size_t)n * pr.cin + c] = pr.weight[(size_t)c * pr.ldw + n];
+            BN_CUDA(cudaMalloc(&d.mb_wpT, wt.size() * sizeof(float)));
+            BN_CUDA(cudaMemcpy(d.mb_wpT, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
         }
         std::vector<float>().swap(op.weight);   // host copy no longer needed
     }
@@ -320,6 +363,8 @@ bn_engine::~bn_engine() {
         if (d.weight) cudaFree(d.weight);
         if (d.bias) cudaFree(d.bias);
         if (d.wpack) cudaFree(d.wpack);
+        if (d.mb_we_pack) cudaFree(d.mb_we_pack);
+        if (d.mb_wpT) cudaFree(d.mb_wpT);
     }
     for (auto* b : d_basis) cudaFree(b);
     for (auto& f : fe_tc) if (f.wpack) cudaFree(f.wpack);
@@ -554,6 +599,45 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
             (p.root(op.out) == p.root(p.logits_tensor) || (p.embedding_tensor >= 0 && p.root(op.out) == p.root(p.embedding_tensor)))) {
             const int ws = wait_for_fetch(c);
             if (ws != BN_OK) return ws;
+        }
+        if (d.mb_group > 0) {
+            // expand -> depthwise -> squeeze-excite -> projection in one kernel (mbconv.cu): E never leaves the SM
+            const PlanOp &dw = p.ops[i + 1], &f1 = p.ops[i + 3], &f2 = p.ops[i + 4], &pr = p.ops[i + 5];
+            if (c->mb_state.empty()) { c->mb_xmaps.resize(p.ops.size()); c->mb_dmaps.resize(p.ops.size()); c->mb_state.assign(p.ops.size(), 0); }
+            const PlanesPtr xp = planes_of(c, op.in), dp = planes_of(c, dw.out);
+            if (c->mb_state[i] == 0) {
+                const uint64_t rows = (uint64_t)std::max<uint64_t>(c->max_batch, 1) * dw.hin * dw.win;
+                const uint32_t box[5] = {64, 64, 1, 1, 1};
+                const uint32_t es[5] = {1, 1, 1, 1, 1};
+                const uint64_t dx[5] = {(uint64_t)op.cin, rows, 1, 1, 2};
+                const uint64_t sx[4] = {(uint64_t)op.cin * 2, rows * op.cin * 2, rows * op.cin * 2, (uint64_t)xp.plane * 2};
+                const uint64_t dd[5] = {(uint64_t)dw.cout, rows, 1, 1, 2};
+                const uint64_t sd[4] = {(uint64_t)dw.cout * 2, rows * dw.cout * 2, rows * dw.cout * 2, (uint64_t)dp.plane * 2};
+                const bool ok = tc_encode_tmap(&c->mb_xmaps[i], xp.hi, dx, sx, box, es, 64) && tc_encode_tmap(&c->mb_dmaps[i], dp.hi, dd, sd, box, es, 64);
+                c->mb_state[i] = ok ? 1 : 2;
+            }
+            if (c->mb_state[i] == 1) {
+                MbconvParams mp{};
+                mp.xmap = c->mb_xmaps[i]; mp.dmap = c->mb_dmaps[i];
+                mp.we_pack = d.mb_we_pack; mp.be = d.bias;
+                mp.wd = e->dev_ops[i + 1].weight; mp.bd = e->dev_ops[i + 1].bias;
+                mp.w1 = e->dev_ops[i + 3].weight; mp.b1 = e->dev_ops[i + 3].bias; mp.ldw1 = f1.ldw;
+                mp.w2 = e->dev_ops[i + 4].weight; mp.b2 = e->dev_ops[i + 4].bias; mp.ldw2 = f2.ldw;
+                mp.wpT = d.mb_wpT; mp.bp = e->dev_ops[i + 5].bias;
+                mp.d_hi = dp.hi; mp.d_plane = dp.plane;
+                if (pr.residual >= 0) { const PlanesPtr rp = planes_of(c, pr.residual); mp.res_hi = rp.hi; mp.res_plane = rp.plane; }
+                const PlanesPtr op_ = planes_of(c, pr.out);
+                mp.out_hi = op_.hi; mp.out_plane = op_.plane;
+                mp.batch = B; mp.h = dw.hin; mp.w = dw.win; mp.k = dw.k; mp.cin = op.cin; mp.cexp = op.cout; mp.cout = pr.cout; mp.r = f1.cout;
+                std::string nm = op.name;
+                const size_t dot = nm.find(".expand");
+                if (dot != std::string::npos) nm = nm.substr(0, dot);
+                prof_mark(c, (nm + ".mbconv").c_str());
+                BN_CUDA(launch_mbconv(mp, e->num_sms, s));
+                ++launches;
+                i += 5;
+                continue;
+            }
         }
         if (op.kind == OP_LINEAR && (int)i == fused_se_fc) {
             prescaled_conv = match_se_tail(p, i);

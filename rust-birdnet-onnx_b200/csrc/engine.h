@@ -14,6 +14,7 @@
 #include "../../include/birdnet_b200.h"
 #include "kernels.h"
 #include "plan.h"
+#include "mbconv.h"
 #include "tc_conv.h"
 
 namespace bn {
@@ -41,6 +42,10 @@ struct DevOp {
     int nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32;
     int halo_slots = 0;          // > 0: TC_IN_HALO (patch staged once, taps as shifted views)
     int epi_warps = 0;           // epilogue warps when the layer runs one CTA per SM (measured per layer class)
+    // fused MBConv block starting at this (expand) op: expand -> depthwise -> pool -> FC -> FC -> projection = ops i .. i+5
+    int mb_group = 0;            // channel group of the fused kernel (0: block runs layer by layer)
+    void* mb_we_pack = nullptr;  // expand weights packed with N tile = mb_group
+    float* mb_wpT = nullptr;     // projection weights [cout][cexp]
 };
 
 struct RangeDev {   // dense per-class tri-state on the device
@@ -132,6 +137,8 @@ struct bn_ctx {
     std::vector<uint8_t> tmap_state;  // 0 = not tried, 1 = ready, 2 = unavailable
     std::vector<CUtensorMap> omaps;   // per plan op: tensor map of its output (TMA-store epilogue)
     std::vector<uint8_t> omap_state;
+    std::vector<CUtensorMap> mb_xmaps, mb_dmaps;   // per plan op (expand op of a fused MBConv block): block input / depthwise output
+    std::vector<uint8_t> mb_state;                 // 0 = not tried, 1 = ready, 2 = unavailable
     float* h_logits = nullptr;   // pinned
     float* h_emb = nullptr;      // pinned
     bn::Pred* d_topk = nullptr;
