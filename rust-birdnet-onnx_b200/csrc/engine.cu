@@ -628,6 +628,8 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
                 if (pr.residual >= 0) { const PlanesPtr rp = planes_of(c, pr.residual); mp.res_hi = rp.hi; mp.res_plane = rp.plane; }
                 const PlanesPtr op_ = planes_of(c, pr.out);
                 mp.out_hi = op_.hi; mp.out_plane = op_.plane;
+                mp.prof = c->profiling && getenv("BN_MB_PROFILE") ? tc_conv_prof_slot((int)i) : nullptr;
+                { static const int dbg = [] { const char* ev = getenv("BN_MB_DEBUG"); return ev ? atoi(ev) : 0; }(); mp.debug = dbg; }
                 mp.batch = B; mp.h = dw.hin; mp.w = dw.win; mp.k = dw.k; mp.cin = op.cin; mp.cexp = op.cout; mp.cout = pr.cout; mp.r = f1.cout;
                 std::string nm = op.name;
                 const size_t dot = nm.find(".expand");

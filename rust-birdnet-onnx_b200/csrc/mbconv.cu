@@ -1,5 +1,5 @@
 // Fused MBConv block (rows A8 of SURVEY.md section 8): 1x1 expand + SiLU -> depthwise kxk + SiLU -> squeeze-excite
-// -> gated 1x1 projection (+ residual), ONE kernel per block, one CTA per segment at a time.
+// -> gated 1x1 projection (+ residual), ONE kernel per block, one CTA (12 worker warps + 1 control warp) per segment at a time.
 //
 //   E = silu(X * We + be)                    [npix][cexp]   tcgen05 into TMEM, never leaves the SM
 //   D = silu(dw_kxk(E) + bd)                 [npix][cexp]   CUDA cores, E read from a shared-memory patch
@@ -13,15 +13,17 @@
 //
 // Phase A, per group of G expanded channels (double-buffered in TMEM, so the MMAs of group g+1 run under the
 // depthwise arithmetic of group g):
-//   one elected thread issues   E_g[npix][G] = X[npix][cin] * We[cin][G]      (hi/lo operands: 3 MMAs per K step, main |
+//   control warp (one lane)     E_g[npix][G] = X[npix][cin] * We[cin][G]      (hi/lo operands: 3 MMAs per K step, main |
 //                                                                             correction accumulators as in tc_conv.cu)
-//   all 16 warps                TMEM -> +bias, SiLU -> FP32 patch [G/2 channel pairs][zero-halo pixels] in smem
-//   all 512 threads             depthwise conv from the patch (thread = channel pair x XB x YB output block, packed
+//   12 worker warps             TMEM -> +bias, SiLU -> FP32 patch [G/2 channel pairs][zero-halo pixels] in smem
+//   384 worker threads          depthwise conv from the patch (thread = channel pair x XB x YB output block, packed
 //                               FFMA2), SiLU, D -> global hi/lo planes, pooled partial sums (fixed order: deterministic)
-// Gate: the two tiny FCs by the whole CTA.
-// Phase B, per 64-channel K chunk (two-stage ring): TMA lands D's hi/lo tiles, all threads build the chunk of
-//   Wp^T * diag(g) as the SWIZZLE_128B [W_hi | W_lo] operand image, one thread issues the MMAs; epilogue adds bias and
-//   the residual and writes the block's output planes.
+// tcgen05.mma issue blocks the issuing thread while the tensor queue is full (measured: ~2.7 k cycles per group when a
+// worker issued), hence the dedicated control warp: the workers never wait behind the tensor pipe.
+// Gate: the two tiny FCs by the workers.
+// Phase B, per 64-channel K chunk (two-stage ring): TMA lands D's hi/lo tiles, the workers build the chunk of
+//   Wp^T * diag(g) as the SWIZZLE_128B [W_hi | W_lo] operand image, the control lane issues the MMAs; epilogue adds bias
+//   and the residual and writes the block's output planes.
 #include "mbconv.h"
 #include "tc_common.cuh"
 
@@ -33,9 +35,13 @@ using namespace tc;
 
 namespace {
 
-constexpr int MB_THREADS = 512;
-constexpr int MB_WARPS = MB_THREADS / 32;
+constexpr int MB_WARPS = 12;                  // worker warps (TMEM reads, depthwise arithmetic, weight images, epilogue)
+constexpr int MB_THREADS = MB_WARPS * 32;
+constexpr int MB_BLOCK = MB_THREADS + 32;     // + one control warp: TMA / bulk loads and every tcgen05.mma issue
 constexpr uint32_t BOX_BYTES = 64 * 128;      // one TMA box: 64 rows x 64 fp16 channels, SWIZZLE_128B
+#ifndef MB_SERIAL_TMEM
+#define MB_SERIAL_TMEM 0                      // 1: issue group g+1 only after the workers' TMEM reads of group g (measured: no gain)
+#endif
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
@@ -46,6 +52,7 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 __device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MB_THREADS) : "memory"); }     // the 12 worker warps only
 __device__ __forceinline__ void arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -68,15 +75,23 @@ __host__ __device__ inline MbLayout mb_layout(int h, int w, int k, int cin, int 
     L.off_xa = 0;
     L.off_we = L.xa_bytes;
     const uint32_t a_end = L.xa_bytes + 2u * L.we_stage + BOX_BYTES;     // + one box: the last M tile may read past its 64 rows
-    L.off_da = 0;
-    L.off_wp = 2u * L.da_stage;
-    const uint32_t b_end = 2u * (L.da_stage + L.wp_stage) + BOX_BYTES;
-    uint32_t o = a_end > b_end ? a_end : b_end;
-    o = (o + 1023u) & ~1023u;
-    L.off_patch = o;
+    // phase A: [X tiles | 2 expand weight stages | patch]; phase B reuses ALL of it (the patch is re-zeroed per segment):
+    // [n_da D stages | 2 projection weight stages], then the FP32 staging tile of the epilogue over the same bytes
+    L.off_patch = (a_end + 1023u) & ~1023u;
     L.patch_bytes = (uint32_t)(G / 2) * (uint32_t)L.npixp * 8u;
-    o += (L.patch_bytes + 15u) & ~15u;
-    L.off_part = o;  o += 2u * (uint32_t)(MB_THREADS / (G / 2)) * (uint32_t)G * 4u;     // pooled partials, double buffered
+    const uint32_t pa_end = L.off_patch + ((L.patch_bytes + 15u) & ~15u);
+    L.stg_pitch = (uint32_t)cout * 4u + 16u;                             // FP32 row + 16 B: conflict-free 16-byte lane stores
+    const uint32_t stg_end = (uint32_t)npix * L.stg_pitch;
+    L.off_da = 0;
+    L.n_da = 3;
+    uint32_t b_end = 3u * L.da_stage + 2u * L.wp_stage + BOX_BYTES;
+    if (b_end > 200u * 1024u) { L.n_da = 2; b_end = 2u * L.da_stage + 2u * L.wp_stage + BOX_BYTES; }
+    L.off_wp = (uint32_t)L.n_da * L.da_stage;
+    uint32_t o = pa_end > b_end ? pa_end : b_end;
+    if (stg_end > o) o = stg_end;
+    o = (o + 1023u) & ~1023u;
+    L.off_wd = o;    o += 2u * (uint32_t)(k * k + 2) * (uint32_t)G * 4u;                // depthwise weights + both biases of a group, double buffered
+    L.off_part = o;  o += 2u * (uint32_t)MB_WARPS * (uint32_t)G * 4u;                   // pooled partials per warp, double buffered
     L.off_pool = o;  o += (uint32_t)cexp * 4u;
     L.off_gate = o;  o += (uint32_t)cexp * 4u;
     L.off_r = o;     o += (uint32_t)((r + 3) & ~3) * 4u;
@@ -85,30 +100,46 @@ __host__ __device__ inline MbLayout mb_layout(int h, int w, int k, int cin, int 
     return L;
 }
 
-template <int K, int G, int XB, int YB>
-__global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant__ MbconvParams p) {
+// K: depthwise kernel size; G: expanded channels per group; XB x YB: output pixels per worker thread;
+// UPT: projection weight units (8 K values of one output channel) per worker thread, cout * 8 <= UPT * MB_THREADS
+template <int K, int G, int XB, int YB, int UPT>
+__global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ MbconvParams p) {
     extern __shared__ __align__(1024) uint8_t mb_smem_raw[];
     __shared__ __align__(8) uint64_t bar_x;          // block input landed
     __shared__ __align__(8) uint64_t bar_w[2];       // expand weights of a group landed (stage = group & 1)
     __shared__ __align__(8) uint64_t bar_e[2];       // expand MMAs of a group complete (TMEM buffer = group & 1)
-    __shared__ __align__(8) uint64_t bar_d[2];       // projection: D chunk landed (stage = chunk & 1)
+    __shared__ __align__(8) uint64_t bar_d[3];       // projection: D chunk landed (stage = chunk % n_da)
     __shared__ __align__(8) uint64_t bar_m[2];       // projection: MMAs of a chunk complete
+    // worker warps -> control lane (one arrive per worker warp); the control warp never joins the workers' barriers
+    __shared__ __align__(8) uint64_t bar_tf[2];      // E buffer read out of TMEM (buffer = group & 1)
+    __shared__ __align__(8) uint64_t bar_wr[2];      // projection weight image of a chunk built (stage = chunk & 1)
+    __shared__ __align__(8) uint64_t bar_dr;         // phase A of the segment done: D stored and fenced
+    __shared__ __align__(8) uint64_t bar_sd;         // segment done: TMEM read by the epilogue
     __shared__ uint32_t tmem_holder;
 
     constexpr int PAD = K / 2;
     constexpr int NP = G / 2;                        // channel pairs per group
-    constexpr int NB = MB_THREADS / NP;              // pixel-block slots
     constexpr int NCOL = XB - 1 + K, NROW = YB - 1 + K;
+    constexpr int SL = G / 16;                       // 16-channel slices per group
+    constexpr int WROWS = K * K + 2;                 // depthwise weight rows + depthwise bias row + expand bias row
+    constexpr int NG4 = MB_WARPS / 4;                // warp groups (one warp per TMEM lane quarter in each)
+    static_assert(MB_WARPS % 4 == 0 && G % 16 == 0, "group = whole 16-channel slices");
+    static_assert(NP == 16 || NP == 32, "a warp holds one or two pixel-block rows of channel pairs");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_ctl = warp == MB_WARPS;            // control warp: one elected lane issues, the rest only keep the barriers
     const int H = p.h, W = p.w, npix = H * W, wp = W + 2 * PAD;
     const int cin = p.cin, cexp = p.cexp, cout = p.cout, R = p.r;
     const MbLayout L = mb_layout(H, W, K, cin, cexp, cout, R, G);
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mb_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic ON the shared array: a round trip through uintptr_t loses the address
+    // space and every access becomes a generic LD / ST (measured: the patch stores alone cost 2.8 k cycles per group)
+    uint8_t* sm = mb_smem_raw + ((1024u - (smem_u32(mb_smem_raw) & 1023u)) & 1023u);
+    float* s_wd = reinterpret_cast<float*>(sm + L.off_wd);
     float* s_part = reinterpret_cast<float*>(sm + L.off_part);
     float* s_pool = reinterpret_cast<float*>(sm + L.off_pool);
     float* s_gate = reinterpret_cast<float*>(sm + L.off_gate);
     float* s_r = reinterpret_cast<float*>(sm + L.off_r);
     float* s_fc = reinterpret_cast<float*>(sm + L.off_fc);
+    const uint32_t wd_u32 = smem_u32(s_wd);
     const int n_grp = cexp / G;
     const int ks_e = (cin + 15) >> 4;                // K steps of the expand GEMM
     const uint32_t e_cols = (uint32_t)L.n_mt * 2u * (uint32_t)G;     // TMEM columns of one E buffer
@@ -117,15 +148,18 @@ __global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant_
 
     if (tid == 0) {
         mbar_init(&bar_x, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_w[i], 1); mbar_init(&bar_e[i], 1); mbar_init(&bar_d[i], 1); mbar_init(&bar_m[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_w[i], 1); mbar_init(&bar_e[i], 1); mbar_init(&bar_d[i], 1); mbar_init(&bar_m[i], 1);
+            mbar_init(&bar_tf[i], MB_WARPS); mbar_init(&bar_wr[i], MB_WARPS);
+        }
+        mbar_init(&bar_d[2], 1);
+        mbar_init(&bar_dr, MB_WARPS);
+        mbar_init(&bar_sd, MB_WARPS);
         fence_barrier_init();
         tma_prefetch_desc(&p.xmap);
         tma_prefetch_desc(&p.dmap);
     }
-    if (warp == 1) tmem_alloc(&tmem_holder, 512);
-    // the patch halo is never written again: zero the whole patch once
-    for (uint32_t i = tid; i < L.patch_bytes / 16u; i += MB_THREADS)
-        reinterpret_cast<uint4*>(sm + L.off_patch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (is_ctl) tmem_alloc(&tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -135,24 +169,38 @@ __global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant_
     const int cp = tid % NP, blk = tid / NP;
     const int xblocks = W / XB;
     const int nblk = (H / YB) * xblocks;
-    const bool dw_active = blk < nblk;
+    const bool dw_active = !is_ctl && blk < nblk;
     const int by = blk / xblocks, oy0 = by * YB, ox0 = (blk - by * xblocks) * XB;
     const float inv_np = 1.0f / (float)npix;
-    // TMEM -> patch mapping: warp = (lane quarter q, M tile m, 16-channel slice of the group)
-    const int q = warp & 3;
-    constexpr int SL = G / 16;                       // 16-channel slices per group
-    static_assert(MB_WARPS % 4 == 0 && G % 16 == 0, "group = whole 16-channel slices");
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    // patch position of this lane's pixel for each of the warp's (at most 4) TMEM units: fixed for the whole kernel
+    int ppix_u[4];
+#pragma unroll
+    for (int ui = 0; ui < 4; ++ui) {
+        const int u = (warp >> 2) + ui * NG4;
+        const int pix = min((u / SL) * 128 + q * 32 + lane, npix - 1);
+        const int y = pix / W, x = pix - y * W;
+        ppix_u[ui] = (y + PAD) * wp + x + PAD;
+    }
 
+    // development aid (p.prof != nullptr): cycles a worker thread of CTA 0 spends per phase, summed over its segments
+    //  [0] segment start  [1] wait E_g  [2] TMEM -> patch + barrier A  [3] depthwise + barrier B  [4] pooled + gate FCs
+    //  [5] projection chunk loop  [6] wait last MMAs  [7] epilogue  [8] pooled + fence + barrier  [9] FC1  [10] segments  [11] total
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 32;
+    unsigned long long pc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = prof ? clock64() : 0;
+    const long long t_start = t_prev;
+    auto tick = [&](int slot) { if (prof) { const long long t = clock64(); pc[slot] += (unsigned long long)(t - t_prev); t_prev = t; } };
     uint32_t gi = 0;        // running group counter: buffers / stages = gi & 1, barrier parity = (gi >> 1) & 1
     uint32_t ck = 0;        // running projection chunk counter
     uint32_t seg_it = 0;
 
-    auto load_we = [&](int g, uint32_t stage) {      // expand weights of group g -> stage (one elected thread)
+    auto load_we = [&](int g, uint32_t stage) {      // expand weights of group g -> stage (control lane)
         arrive_expect_tx(&bar_w[stage], L.we_stage);
         bulk_copy_g2s(sm + L.off_we + stage * L.we_stage, reinterpret_cast<const uint8_t*>(p.we_pack) + (size_t)g * L.we_stage,
                       L.we_stage, &bar_w[stage]);
     };
-    auto issue_expand = [&](uint32_t gcount) {       // MMAs of the group with running index gcount (one elected thread)
+    auto issue_expand = [&](uint32_t gcount) {       // MMAs of the group with running index gcount (control lane)
         const uint32_t b = gcount & 1u;
         const uint32_t idesc2 = umma_idesc_f16(128, 2 * G), idesc1 = umma_idesc_f16(128, G);
         for (int m = 0; m < L.n_mt; ++m) {
@@ -169,11 +217,103 @@ __global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant_
         }
         umma_commit(&bar_e[b]);
     };
+    // depthwise weights + both biases of group g -> s_wd[buf] (cp.async, 16-byte units; every worker commits a group)
+    auto load_wd = [&](int g, uint32_t buf) {
+        constexpr int UNITS = WROWS * (G / 4);
+        for (int i = tid; i < UNITS; i += MB_THREADS) {
+            const int row = i / (G / 4), ch = i - row * (G / 4);
+            const float* src = (row < K * K ? p.wd + (size_t)row * cexp : (row == K * K ? p.bd : p.be)) + g * G + ch * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wd_u32 + (uint32_t)((buf * WROWS + row) * G + ch * 4) * 4u), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // projection weights of chunk kc for this thread's units -> registers (the L2 latency is spent before the waits)
+    auto load_wp = [&](int kc, float4 (&wr)[UPT][2]) {
+#pragma unroll
+        for (int i = 0; i < UPT; ++i) {
+            const int u = tid + i * MB_THREADS;
+            const int n = u >> 3, c0 = kc * 64 + (u & 7) * 8;
+            if (u < cout * 8 && c0 < cexp) {                 // cexp is a multiple of 8
+                const float4* src = reinterpret_cast<const float4*>(p.wpT + (size_t)n * cexp + c0);
+                wr[i][0] = __ldg(src);
+                wr[i][1] = __ldg(src + 1);
+            } else {
+                wr[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                wr[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    // ... scaled by the gate -> [W_hi | W_lo] operand image of stage st (row n = output channel, 64 K values)
+    auto store_wp = [&](int kc, uint32_t st, const float4 (&wr)[UPT][2]) {
+        uint8_t* wst = sm + L.off_wp + st * L.wp_stage;
+#pragma unroll
+        for (int i = 0; i < UPT; ++i) {
+            const int u = tid + i * MB_THREADS;
+            if (u < cout * 8) {
+                const int n = u >> 3, ku = u & 7;
+                const int c0 = kc * 64 + ku * 8;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (c0 < cexp) {
+                    const float4 g0 = *reinterpret_cast<const float4*>(s_gate + c0), g1 = *reinterpret_cast<const float4*>(s_gate + c0 + 4);
+                    v[0] = wr[i][0].x * g0.x; v[1] = wr[i][0].y * g0.y; v[2] = wr[i][0].z * g0.z; v[3] = wr[i][0].w * g0.w;
+                    v[4] = wr[i][1].x * g1.x; v[5] = wr[i][1].y * g1.y; v[6] = wr[i][1].z * g1.z; v[7] = wr[i][1].w * g1.w;
+                }
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)ku);
+                *reinterpret_cast<uint4*>(wst + off) = hi;
+                *reinterpret_cast<uint4*>(wst + (uint32_t)cout * 128u + off) = lo;
+            }
+        }
+    };
+    auto load_d = [&](int seg, int kc, uint32_t st) {    // D chunk kc of this segment -> stage st (control lane)
+        arrive_expect_tx(&bar_d[st], L.da_stage);
+        for (int pl = 0; pl < 2; ++pl)
+            for (int bx = 0; bx < L.n_box; ++bx)
+                tma_load_5d(sm + L.off_da + st * L.da_stage + ((uint32_t)pl * (uint32_t)L.n_box + (uint32_t)bx) * BOX_BYTES, &p.dmap,
+                            kc * 64, seg * npix + bx * 64, 0, 0, pl, &bar_d[st]);
+    };
+    const uint32_t idescP2 = umma_idesc_f16(128, fused_n ? 2 * cout : cout), idescP1 = umma_idesc_f16(128, cout);
+    auto issue_project = [&](int kc, uint32_t st, uint32_t sd) {   // MMAs of projection chunk kc: weight stage st, D stage sd (control lane)
+        const int ksn = min(4, (cexp - kc * 64 + 15) >> 4);
+        const uint32_t wb = smem_u32(sm + L.off_wp) + st * L.wp_stage;
+        for (int m = 0; m < L.n_mt; ++m) {
+            const uint32_t acc = tmem_base + (uint32_t)m * p_cols;
+            const uint32_t a_hi = smem_u32(sm + L.off_da) + sd * L.da_stage + (2u * (uint32_t)m) * BOX_BYTES;
+            const uint32_t a_lo = a_hi + (uint32_t)L.n_box * BOX_BYTES;
+            for (int j = 0; j < ksn; ++j) {
+                const uint64_t dk = (uint64_t)(kDescKStep * j);
+                const uint32_t accf = (kc | j) != 0 ? 1u : 0u;
+                if (fused_n) {
+                    umma_f16(acc, umma_desc_sw128(a_hi) + dk, umma_desc_sw128(wb) + dk, idescP2, accf);
+                } else {
+                    umma_f16(acc, umma_desc_sw128(a_hi) + dk, umma_desc_sw128(wb) + dk, idescP1, accf);
+                    umma_f16(acc + (uint32_t)cout, umma_desc_sw128(a_hi) + dk, umma_desc_sw128(wb + (uint32_t)cout * 128u) + dk, idescP1, accf);
+                }
+                umma_f16(acc + (uint32_t)cout, umma_desc_sw128(a_lo) + dk, umma_desc_sw128(wb) + dk, idescP1, 1u);
+            }
+        }
+        umma_commit(&bar_m[st]);
+    };
+    // pooled mean of a finished group from the per-warp partials, fixed summation order (the last G worker threads)
+    auto pooled_mean = [&](int g, uint32_t buf) {
+        if (!is_ctl && tid >= MB_THREADS - G) {
+            const int ch = tid - (MB_THREADS - G);
+            const float* part = s_part + (size_t)buf * MB_WARPS * G + ch;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < MB_WARPS; i += 4) { s0 += part[i * G]; s1 += part[(i + 1) * G]; s2 += part[(i + 2) * G]; s3 += part[(i + 3) * G]; }
+            s_pool[g * G + ch] = ((s0 + s1) + (s2 + s3)) * inv_np;
+        }
+    };
 
-    for (int seg = blockIdx.x; seg < p.batch; seg += gridDim.x, ++seg_it) {
-        // ================================ phase A ================================
-        if (warp == 0) {
-            if (elect_one()) {
+    if (is_ctl) {
+        // =========================== control warp: TMA, bulk copies, every tcgen05.mma ===========================
+        if (elect_one()) {
+            for (int seg = blockIdx.x; seg < p.batch; seg += gridDim.x, ++seg_it) {
+                // previous segment: its epilogue has read TMEM (bar_sd) and all its MMAs have retired (waited below)
+                if (seg_it > 0) mbar_wait(&bar_sd, (seg_it - 1u) & 1u);
+                tc_fence_after();
                 arrive_expect_tx(&bar_x, L.xa_bytes);
                 for (int kc = 0; kc < L.kc_e; ++kc)
                     for (int pl = 0; pl < 2; ++pl)
@@ -183,72 +323,117 @@ __global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant_
                 load_we(0, gi & 1u);
                 if (n_grp > 1) load_we(1, (gi + 1u) & 1u);
                 mbar_wait(&bar_x, seg_it & 1u);
-                mbar_wait(&bar_w[gi & 1u], (gi >> 1) & 1u);
-                tc_fence_after();
-                issue_expand(gi);
+                for (int g = 0; g < n_grp; ++g, ++gi) {
+                    const uint32_t b = gi & 1u;
+                    // the workers have read group gi - 1 out of TMEM (which implies group gi - 2, the previous user of
+                    // buffer b): MMAs issued earlier would sit in front of their tcgen05.ld in the tensor pipe
+                    if (MB_SERIAL_TMEM ? gi >= 1u : gi >= 2u) {
+                        const uint32_t w = MB_SERIAL_TMEM ? gi - 1u : gi - 2u;
+                        mbar_wait(&bar_tf[w & 1u], (w >> 1) & 1u);
+                    }
+                    mbar_wait(&bar_w[b], (gi >> 1) & 1u);
+                    tc_fence_after();
+                    issue_expand(gi);
+                    // the weight stage of group gi - 1 is free once its MMAs have retired: fetch group g + 1 into it
+                    if (g >= 1 && g + 1 < n_grp) {
+                        mbar_wait(&bar_e[b ^ 1u], ((gi - 1u) >> 1) & 1u);
+                        load_we(g + 1, b ^ 1u);
+                    }
+                }
+                // every expand MMA retired -> the operand region may take the projection's stages
+                mbar_wait(&bar_e[(gi - 1u) & 1u], ((gi - 1u) >> 1) & 1u);
+                if (n_grp > 1) mbar_wait(&bar_e[gi & 1u], ((gi - 2u) >> 1) & 1u);
+                mbar_wait(&bar_dr, seg_it & 1u);                     // D stored and fenced by every worker
+                const uint32_t nda = (uint32_t)L.n_da;
+                for (uint32_t i = 0; i < nda && (int)i < L.kc_p; ++i) load_d(seg, (int)i, (ck + i) % nda);
+                for (int kc = 0; kc < L.kc_p; ++kc, ++ck) {
+                    const uint32_t st = ck & 1u, sd = ck % nda;
+                    mbar_wait(&bar_wr[st], (ck >> 1) & 1u);          // weight image of chunk kc built
+                    mbar_wait(&bar_d[sd], (ck / nda) & 1u);          // D tiles of chunk kc landed
+                    tc_fence_after();
+                    issue_project(kc, st, sd);
+                    // chunk kc - 1 retired -> its D stage takes chunk kc - 1 + n_da (the first n_da chunks are in flight already)
+                    if (kc >= 1 && kc - 1 + (int)nda < L.kc_p) {
+                        mbar_wait(&bar_m[st ^ 1u], ((ck - 1u) >> 1) & 1u);
+                        load_d(seg, kc - 1 + (int)nda, (ck - 1u) % nda);
+                    }
+                }
             }
-            __syncwarp();
         }
+        __syncwarp();
+    } else {
+    // ================================================ workers ================================================
+    for (int seg = blockIdx.x; seg < p.batch; seg += gridDim.x, ++seg_it) {
+        // ================================ phase A ================================
+        load_wd(0, gi & 1u);
+        // the projection stages and the epilogue tile of the previous segment lay over the patch: zero it (halo included)
+        for (uint32_t i = tid; i < L.patch_bytes / 16u; i += MB_THREADS)
+            reinterpret_cast<uint4*>(sm + L.off_patch)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        worker_sync();                                               // patch zeroed, group 0's depthwise weights + biases visible
+        tick(0);
         for (int g = 0; g < n_grp; ++g, ++gi) {
             const uint32_t b = gi & 1u;
-            // (0) the next group's MMAs go to the other TMEM buffer (free since the barrier after the previous group's
-            //     TMEM reads) and run under this group's depthwise arithmetic
-            if (warp == 0) {
-                if (g + 1 < n_grp && elect_one()) {
-                    mbar_wait(&bar_w[b ^ 1u], ((gi + 1u) >> 1) & 1u);
-                    tc_fence_after();
-                    issue_expand(gi + 1u);
-                }
-                __syncwarp();
-            }
-            // (1) E_g complete -> its weight stage is free again: fetch group g + 2 into it
+            if (g + 1 < n_grp) load_wd(g + 1, b ^ 1u);               // next group's depthwise weights + biases
+            const float* wgrp = s_wd + (size_t)b * WROWS * G;
             mbar_wait(&bar_e[b], (gi >> 1) & 1u);
             tc_fence_after();
-            if (warp == 0) {
-                if (g + 2 < n_grp && elect_one()) load_we(g + 2, b);
-                __syncwarp();
-            }
-            // TMEM -> bias, SiLU -> patch.  warp (q, m, slice): rows m*128 + q*32 + lane, channels slice*16 .. +15
-            for (int u = warp >> 2; u < L.n_mt * SL; u += MB_WARPS / 4) {
+            tick(1);
+            // TMEM -> + expand bias, SiLU -> patch.  warp (q, unit): rows m*128 + q*32 + lane, channels slice*16 .. +15
+#pragma unroll
+            for (int ui = 0; ui < 4; ++ui) {
+                const int u = (warp >> 2) + ui * NG4;
+                if (ui * NG4 >= 2 * SL) break;                       // compile-time bound: n_mt <= 2
                 const int m = u / SL, sl = u - m * SL;
                 const int pix = m * 128 + q * 32 + lane;
-                if (m * 128 + q * 32 < npix) {                       // warp-uniform: this quarter holds real rows
+                if (u < L.n_mt * SL && m * 128 + q * 32 < npix) {    // warp-uniform: a real unit whose quarter holds real rows
                     uint32_t rm[16], rc[16];
                     const uint32_t t = tmem_base + b * e_cols + (uint32_t)m * 2u * (uint32_t)G + (uint32_t)(sl * 16) + ((uint32_t)(q * 32) << 16);
-                    tmem_ld16_nowait(t, rm);
-                    tmem_ld16_nowait(t + (uint32_t)G, rc);
-                    tmem_ld_wait();
-                    if (pix < npix) {
-                        const int y = pix / W, x = pix - y * W;
-                        const int ppix = (y + PAD) * wp + x + PAD;
-                        const float* be = p.be + g * G + sl * 16;
+                    if (!(p.debug & 4)) {
+                        tmem_ld16_nowait(t, rm);
+                        tmem_ld16_nowait(t + (uint32_t)G, rc);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { rm[j] = (uint32_t)(lane + j); rc[j] = 0u; }
+                    }
+                    if (pix < npix && !(p.debug & 2)) {
+                        const int ppix = ppix_u[ui];
+                        const float2* be = reinterpret_cast<const float2*>(wgrp + (K * K + 1) * G + sl * 16);
                         float2* dst = reinterpret_cast<float2*>(sm + L.off_patch) + (size_t)(sl * 8) * L.npixp + ppix;
+                        float2 bq[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bq[j] = be[j];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float2 bb = __ldg(reinterpret_cast<const float2*>(be) + j);
-                            const float v0 = silu_f(__uint_as_float(rm[2 * j]) + __uint_as_float(rc[2 * j]) + bb.x);
-                            const float v1 = silu_f(__uint_as_float(rm[2 * j + 1]) + __uint_as_float(rc[2 * j + 1]) + bb.y);
+                            const float2 bb = bq[j];
+                            float v0 = __uint_as_float(rm[2 * j]) + __uint_as_float(rc[2 * j]) + bb.x;
+                            float v1 = __uint_as_float(rm[2 * j + 1]) + __uint_as_float(rc[2 * j + 1]) + bb.y;
+                            if (!(p.debug & 1)) { v0 = silu_f(v0); v1 = silu_f(v1); }
                             dst[(size_t)j * L.npixp] = make_float2(v0, v1);
                         }
                     }
                 }
             }
+            // this warp has read its share of E_g out of TMEM: tell the control lane (buffer b may be overwritten)
             tc_fence_before();
-            __syncthreads();                                         // (2) patch complete, TMEM buffer b free
-            if (g > 0 && tid < G) {                                  // pooled mean of the previous group, fixed order
-                const float* part = s_part + (size_t)(b ^ 1u) * NB * G;
-                float s = 0.f;
-                for (int i = 0; i < NB; ++i) s += part[i * G + tid];
-                s_pool[(g - 1) * G + tid] = s * inv_np;
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tf[b]);
+            worker_sync();                                           // A: patch complete
+            tick(2);
+            if (g > 0) pooled_mean(g - 1, b ^ 1u);
             // depthwise conv + SiLU -> D planes (un-gated), pooled partial sums
             float2 pool = make_float2(0.f, 0.f);
-            if (dw_active) {
+            if (dw_active && !(p.debug & 32)) {
                 const int c = g * G + 2 * cp;
+                // this thread's depthwise weights (visible since the previous barrier B)
                 unsigned long long wk[K * K];
+                {
+                    const float* wb = wgrp + 2 * cp;
 #pragma unroll
-                for (int i = 0; i < K * K; ++i) wk[i] = __ldg(reinterpret_cast<const unsigned long long*>(p.wd + (size_t)i * cexp + c));
-                const unsigned long long bias = __ldg(reinterpret_cast<const unsigned long long*>(p.bd + c));
+                    for (int i = 0; i < K * K; ++i) wk[i] = *reinterpret_cast<const unsigned long long*>(wb + i * G);
+                }
+                const unsigned long long bias = *reinterpret_cast<const unsigned long long*>(wgrp + K * K * G + 2 * cp);
                 unsigned long long acc[YB][XB];
 #pragma unroll
                 for (int y = 0; y < YB; ++y)
@@ -278,9 +463,11 @@ __global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant_
                 for (int y = 0; y < YB; ++y)
 #pragma unroll
                     for (int j = 0; j < XB; ++j) {
-                        const float v0 = silu_f(lo_f(acc[y][j])), v1 = silu_f(hi_f(acc[y][j]));
+                        float v0 = lo_f(acc[y][j]), v1 = hi_f(acc[y][j]);
+                        if (!(p.debug & 16)) { v0 = silu_f(v0); v1 = silu_f(v1); }
                         pool.x += v0;
                         pool.y += v1;
+                        if (p.debug & 8) continue;
                         const __half2 hh = __floats2half2_rn(v0, v1);
                         const float2 bk = __half22float2(hh);
                         const __half2 ll = __floats2half2_rn(v0 - bk.x, v1 - bk.y);
@@ -289,192 +476,195 @@ __global__ void __launch_bounds__(MB_THREADS, 1) k_mbconv(const __grid_constant_
                         *reinterpret_cast<__half2*>(dh + p.d_plane + o) = ll;
                     }
             }
-            reinterpret_cast<float2*>(s_part + (size_t)b * NB * G)[blk * NP + cp] = pool;
-            __syncthreads();                                         // (3) patch free, partials visible
+            // per-warp partial of the pooled sums: a warp holds 32 / NP pixel-block rows of the same NP channel pairs
+            if (NP == 16) {
+                pool.x += __shfl_xor_sync(0xffffffffu, pool.x, 16);
+                pool.y += __shfl_xor_sync(0xffffffffu, pool.y, 16);
+            }
+            if (lane < NP) reinterpret_cast<float2*>(s_part + (size_t)b * MB_WARPS * G)[warp * NP + cp] = pool;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");     // next group's weights have landed (this thread's copies)
+            worker_sync();                                           // B: patch free, partials + next weights visible
+            tick(3);
         }
-        if (tid < G) {                                               // last group's pooled mean
-            const float* part = s_part + (size_t)((gi - 1u) & 1u) * NB * G;
-            float s = 0.f;
-            for (int i = 0; i < NB; ++i) s += part[i * G + tid];
-            s_pool[(n_grp - 1) * G + tid] = s * inv_np;
-        }
+        pooled_mean(n_grp - 1, (gi - 1u) & 1u);
         fence_proxy_async_all();                                     // this thread's D stores -> visible to the TMA engine
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_dr);                         // control: D of this segment may be fetched
+        float4 wr[UPT][2];
+        load_wp(0, wr);
+        worker_sync();                                               // pooled vector complete
+        tick(8);
 
         // ================================ gate ================================
         {
-            const int cpw = (cexp + MB_WARPS - 1) / MB_WARPS;       // FC1: warps split the channels, lanes = output j
+            // FC1: r = silu(W1^T pooled + b1).  A warp takes a slice of the channels; 8 lanes cover one row of W1 with
+            // float4 loads (R <= 32 of its ldw1 floats), 4 rows per step, up to 64 rows of the slice in flight at once.
+            const int cpw = (cexp + MB_WARPS - 1) / MB_WARPS;
             const int cbeg = warp * cpw, cend = min(cexp, cbeg + cpw);
+            const int l8 = lane & 7, rsub = lane >> 3;
             for (int j0 = 0; j0 < R; j0 += 32) {
-                const int j = j0 + lane;
-                if (j < R) {
-                    float a = 0.f;
-                    int cc = cbeg;
-                    for (; cc + 8 <= cend; cc += 8) {
-                        float wv[8];
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool col_ok = j0 + 4 * l8 < p.ldw1;            // ldw1 is R rounded up to 4: the pad columns are zero
+                for (int c0 = cbeg; c0 < cend; c0 += 64) {
+                    float4 wv[16];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) wv[u] = __ldg(p.w1 + (size_t)(cc + u) * p.ldw1 + j);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) a = fmaf(s_pool[cc + u], wv[u], a);
+                    for (int i = 0; i < 16; ++i) {
+                        const int cc = c0 + 4 * i + rsub;
+                        wv[i] = (col_ok && cc < cend) ? __ldg(reinterpret_cast<const float4*>(p.w1 + (size_t)cc * p.ldw1 + j0) + l8) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    for (; cc < cend; ++cc) a = fmaf(s_pool[cc], __ldg(p.w1 + (size_t)cc * p.ldw1 + j), a);
-                    s_fc[warp * R + j] = a;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int cc = c0 + 4 * i + rsub;
+                        const float pv = cc < cend ? s_pool[cc] : 0.f;
+                        a4.x = fmaf(pv, wv[i].x, a4.x); a4.y = fmaf(pv, wv[i].y, a4.y); a4.z = fmaf(pv, wv[i].z, a4.z); a4.w = fmaf(pv, wv[i].w, a4.w);
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {                  // add the 4 row lanes (fixed order)
+                    a4.x += __shfl_xor_sync(0xffffffffu, a4.x, o); a4.y += __shfl_xor_sync(0xffffffffu, a4.y, o);
+                    a4.z += __shfl_xor_sync(0xffffffffu, a4.z, o); a4.w += __shfl_xor_sync(0xffffffffu, a4.w, o);
+                }
+                if (rsub == 0) {
+                    const int j = j0 + 4 * l8;
+                    if (j + 0 < R) s_fc[warp * R + j + 0] = a4.x;
+                    if (j + 1 < R) s_fc[warp * R + j + 1] = a4.y;
+                    if (j + 2 < R) s_fc[warp * R + j + 2] = a4.z;
+                    if (j + 3 < R) s_fc[warp * R + j + 3] = a4.w;
                 }
             }
-            __syncthreads();
+            worker_sync();
             for (int j = tid; j < R; j += MB_THREADS) {
-                float v = p.b1[j];
+                float v = __ldg(p.b1 + j);
 #pragma unroll
                 for (int wi = 0; wi < MB_WARPS; ++wi) v += s_fc[wi * R + j];
                 s_r[j] = v * (1.0f / (1.0f + expf(-v)));
             }
-            __syncthreads();
-            for (int cc = tid; cc < cexp; cc += MB_THREADS) {       // FC2: thread per channel, rows of W2 contiguous in c
-                float v = p.b2[cc];
-                int j = 0;
-                for (; j + 8 <= R; j += 8) {
-                    float wv[8];
+            worker_sync();
+            tick(9);
+            // FC2: g = sigmoid(W2^T r + b2): a thread takes channels tid and tid + 384 together (rows of W2 are contiguous in
+            // c: coalesced), 2 x 12 loads in flight per step
+            for (int cb = 0; cb < cexp; cb += 2 * MB_THREADS) {
+                const int c0 = cb + tid, c1 = cb + tid + MB_THREADS;
+                const bool ok0 = c0 < cexp, ok1 = c1 < cexp;
+                float v0 = ok0 ? __ldg(p.b2 + c0) : 0.f, v1 = ok1 ? __ldg(p.b2 + c1) : 0.f;
+                for (int j = 0; j < R; j += 12) {
+                    float w0[12], w1v[12];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) wv[u] = __ldg(p.w2 + (size_t)(j + u) * p.ldw2 + cc);
+                    for (int u = 0; u < 12; ++u) {
+                        const bool jo = j + u < R;
+                        w0[u] = (jo && ok0) ? __ldg(p.w2 + (size_t)(j + u) * p.ldw2 + c0) : 0.f;
+                        w1v[u] = (jo && ok1) ? __ldg(p.w2 + (size_t)(j + u) * p.ldw2 + c1) : 0.f;
+                    }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v = fmaf(s_r[j + u], wv[u], v);
+                    for (int u = 0; u < 12; ++u) {
+                        const float rv = j + u < R ? s_r[j + u] : 0.f;
+                        v0 = fmaf(rv, w0[u], v0);
+                        v1 = fmaf(rv, w1v[u], v1);
+                    }
                 }
-                for (; j < R; ++j) v = fmaf(s_r[j], __ldg(p.w2 + (size_t)j * p.ldw2 + cc), v);
-                s_gate[cc] = 1.0f / (1.0f + expf(-v));
+                if (ok0) s_gate[c0] = 1.0f / (1.0f + expf(-v0));
+                if (ok1) s_gate[c1] = 1.0f / (1.0f + expf(-v1));
             }
-            __syncthreads();
+            worker_sync();
         }
+        tick(4);
 
         // ================================ phase B: Y = (D * g) * Wp ================================
-        const uint32_t idescP2 = umma_idesc_f16(128, fused_n ? 2 * cout : cout), idescP1 = umma_idesc_f16(128, cout);
+        // chunk kc: stage st = ck & 1.  The workers build the weight image of chunk kc while the MMAs of chunk kc - 1 run;
+        // the control lane issues chunk kc as soon as the image (bar_wr) and the D tiles (bar_d) are there.
         for (int kc = 0; kc < L.kc_p; ++kc, ++ck) {
-            const uint32_t s = ck & 1u;
-            // stage s is free when the MMAs of chunk ck - 2 have retired
-            if (ck >= 2u) mbar_wait(&bar_m[s], ((ck >> 1) - 1u) & 1u);
-            if (warp == 0) {
-                if (elect_one()) {
-                    arrive_expect_tx(&bar_d[s], L.da_stage);
-                    for (int pl = 0; pl < 2; ++pl)
-                        for (int bx = 0; bx < L.n_box; ++bx)
-                            tma_load_5d(sm + L.off_da + s * L.da_stage + ((uint32_t)pl * (uint32_t)L.n_box + (uint32_t)bx) * BOX_BYTES, &p.dmap,
-                                        kc * 64, seg * npix + bx * 64, 0, 0, pl, &bar_d[s]);
-                }
-                __syncwarp();
-            }
-            // Wp^T chunk scaled by the gate -> [W_hi | W_lo] operand image (row n = output channel, 64 K values)
-            uint8_t* wst = sm + L.off_wp + s * L.wp_stage;
-            for (int u = tid; u < cout * 8; u += MB_THREADS) {
-                const int n = u >> 3, ku = u & 7;
-                const int c0 = kc * 64 + ku * 8;
-                float v[8];
-                if (c0 < cexp) {                                     // cexp is a multiple of 8
-                    const float4* src = reinterpret_cast<const float4*>(p.wpT + (size_t)n * cexp + c0);
-                    const float4 a = __ldg(src), bq = __ldg(src + 1);
-                    const float4 g0 = *reinterpret_cast<const float4*>(s_gate + c0), g1 = *reinterpret_cast<const float4*>(s_gate + c0 + 4);
-                    v[0] = a.x * g0.x; v[1] = a.y * g0.y; v[2] = a.z * g0.z; v[3] = a.w * g0.w;
-                    v[4] = bq.x * g1.x; v[5] = bq.y * g1.y; v[6] = bq.z * g1.z; v[7] = bq.w * g1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                }
-                uint4 hi, lo;
-                split8(v, hi, lo);
-                const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)ku);
-                *reinterpret_cast<uint4*>(wst + off) = hi;
-                *reinterpret_cast<uint4*>(wst + (uint32_t)cout * 128u + off) = lo;
-            }
+            const uint32_t st = ck & 1u;
+            if (kc >= 2) mbar_wait(&bar_m[st], ((ck - 2u) >> 1) & 1u);   // the stage's previous chunk has retired
+            store_wp(kc, st, wr);
+            if (kc + 1 < L.kc_p) load_wp(kc + 1, wr);
             fence_proxy_async_smem();
-            __syncthreads();
-            if (warp == 0) {
-                if (elect_one()) {
-                    mbar_wait(&bar_d[s], (ck >> 1) & 1u);
-                    tc_fence_after();
-                    const int ksn = min(4, (cexp - kc * 64 + 15) >> 4);
-                    for (int m = 0; m < L.n_mt; ++m) {
-                        const uint32_t acc = tmem_base + (uint32_t)m * p_cols;
-                        const uint32_t a_hi = smem_u32(sm + L.off_da) + s * L.da_stage + (2u * (uint32_t)m) * BOX_BYTES;
-                        const uint32_t a_lo = a_hi + (uint32_t)L.n_box * BOX_BYTES;
-                        const uint32_t wb = smem_u32(wst);
-                        for (int j = 0; j < ksn; ++j) {
-                            const uint64_t dk = (uint64_t)(kDescKStep * j);
-                            const uint32_t accf = (kc | j) != 0 ? 1u : 0u;
-                            if (fused_n) {
-                                umma_f16(acc, umma_desc_sw128(a_hi) + dk, umma_desc_sw128(wb) + dk, idescP2, accf);
-                            } else {
-                                umma_f16(acc, umma_desc_sw128(a_hi) + dk, umma_desc_sw128(wb) + dk, idescP1, accf);
-                                umma_f16(acc + (uint32_t)cout, umma_desc_sw128(a_hi) + dk, umma_desc_sw128(wb + (uint32_t)cout * 128u) + dk, idescP1, accf);
-                            }
-                            umma_f16(acc + (uint32_t)cout, umma_desc_sw128(a_lo) + dk, umma_desc_sw128(wb) + dk, idescP1, 1u);
-                        }
-                    }
-                    umma_commit(&bar_m[s]);
-                }
-                __syncwarp();
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_wr[st]);
         }
-        // every chunk's MMAs complete (commits arrive in order: the last one covers all)
+        tick(5);
+        // every chunk's MMAs complete (commits retire in order; both stages are waited so the parities stay in step)
         {
             const uint32_t last = ck - 1u;
-            mbar_wait(&bar_m[last & 1u], (last >> 1) & 1u);
             if (L.kc_p >= 2) { const uint32_t prev = ck - 2u; mbar_wait(&bar_m[prev & 1u], (prev >> 1) & 1u); }
+            mbar_wait(&bar_m[last & 1u], (last >> 1) & 1u);
             tc_fence_after();
         }
-        // epilogue: main + correction + bias (+ residual) -> hi/lo planes.  warp = (q, m, column slices)
+        tick(6);
+        // epilogue, pass 1: main + correction + bias -> FP32 staging tile [npix][cout] in the (now idle) operand region.
+        // warp = (q, unit = M tile x 16-column slice), lane = row; row pitch + 16 B keeps the 16-byte lane stores conflict-free
         {
             const int n_sl = cout >> 4;
-            for (int u = warp >> 2; u < L.n_mt * n_sl; u += MB_WARPS / 4) {
+            for (int u = warp >> 2; u < L.n_mt * n_sl; u += NG4) {
                 const int m = u / n_sl, sl = u - m * n_sl;
                 if (m * 128 + q * 32 >= npix) continue;              // warp-uniform
                 const int pix = m * 128 + q * 32 + lane;
+                const int n0 = sl * 16;
                 uint32_t rm[16], rc[16];
                 const uint32_t t = tmem_base + (uint32_t)m * p_cols + (uint32_t)(sl * 16) + ((uint32_t)(q * 32) << 16);
                 tmem_ld16_nowait(t, rm);
                 tmem_ld16_nowait(t + (uint32_t)cout, rc);
                 tmem_ld_wait();
                 if (pix < npix) {
-                    const int n0 = sl * 16;
-                    float v[16];
+                    float4* dst = reinterpret_cast<float4*>(sm + (size_t)pix * L.stg_pitch + (size_t)n0 * 4);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
                         const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bp + n0) + j4);
-                        v[4 * j4 + 0] = __uint_as_float(rm[4 * j4 + 0]) + __uint_as_float(rc[4 * j4 + 0]) + bv.x;
-                        v[4 * j4 + 1] = __uint_as_float(rm[4 * j4 + 1]) + __uint_as_float(rc[4 * j4 + 1]) + bv.y;
-                        v[4 * j4 + 2] = __uint_as_float(rm[4 * j4 + 2]) + __uint_as_float(rc[4 * j4 + 2]) + bv.z;
-                        v[4 * j4 + 3] = __uint_as_float(rm[4 * j4 + 3]) + __uint_as_float(rc[4 * j4 + 3]) + bv.w;
+                        dst[j4] = make_float4(__uint_as_float(rm[4 * j4 + 0]) + __uint_as_float(rc[4 * j4 + 0]) + bv.x,
+                                              __uint_as_float(rm[4 * j4 + 1]) + __uint_as_float(rc[4 * j4 + 1]) + bv.y,
+                                              __uint_as_float(rm[4 * j4 + 2]) + __uint_as_float(rc[4 * j4 + 2]) + bv.z,
+                                              __uint_as_float(rm[4 * j4 + 3]) + __uint_as_float(rc[4 * j4 + 3]) + bv.w);
                     }
-                    const size_t o = ((size_t)seg * npix + pix) * cout + n0;
-                    if (p.res_hi) {
-#pragma unroll
-                        for (int j2 = 0; j2 < 2; ++j2) {
-                            const uint4 qh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o) + j2);
-                            const uint4 ql = __ldg(reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + o) + j2);
-                            const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
-                            const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 a = __half22float2(h2[e]), d = __half22float2(l2[e]);
-                                v[8 * j2 + 2 * e] += a.x + d.x;
-                                v[8 * j2 + 2 * e + 1] += a.y + d.y;
-                            }
-                        }
-                    }
-                    uint4 hq[2], lq[2];
-                    split8(v, hq[0], lq[0]);
-                    split8(v + 8, hq[1], lq[1]);
-                    uint4* oh = reinterpret_cast<uint4*>(p.out_hi + o);
-                    uint4* ol = reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o);
-                    oh[0] = hq[0]; oh[1] = hq[1];
-                    ol[0] = lq[0]; ol[1] = lq[1];
                 }
             }
         }
+        // TMEM is read out: the control lane may start the next segment's expand MMAs ... but NOT its TMA loads into the
+        // operand region, which the staging tile occupies until pass 2 is over: bar_sd is signalled after pass 2.
         tc_fence_before();
-        __syncthreads();               // TMEM and the shared operand region are free for the next segment
-        tc_fence_after();
+        worker_sync();
+        // pass 2: (+ residual) -> hi/lo split -> planes, 8 channels (16 bytes per plane) per thread, rows contiguous: coalesced
+        {
+            const int upr = cout >> 3;                               // 8-channel units per row
+            const int total = npix * upr;
+            for (int u = tid; u < total; u += MB_THREADS) {
+                const int pix = u / upr, n0 = (u - pix * upr) * 8;
+                const float4* src = reinterpret_cast<const float4*>(sm + (size_t)pix * L.stg_pitch + (size_t)n0 * 4);
+                const float4 a = src[0], bq4 = src[1];
+                float v[8] = {a.x, a.y, a.z, a.w, bq4.x, bq4.y, bq4.z, bq4.w};
+                const size_t o = ((size_t)seg * npix + pix) * cout + n0;
+                if (p.res_hi) {
+                    const uint4 qh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
+                    const uint4 ql = __ldg(reinterpret_cast<const uint4*>(p.res_hi + p.res_plane + o));
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
+                    const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 x = __half22float2(h2[e]), d = __half22float2(l2[e]);
+                        v[2 * e] += x.x + d.x;
+                        v[2 * e + 1] += x.y + d.y;
+                    }
+                }
+                uint4 hq, lq;
+                split8(v, hq, lq);
+                *reinterpret_cast<uint4*>(p.out_hi + o) = hq;
+                *reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o) = lq;
+            }
+        }
+        // this warp is done with TMEM, the staging tile and the segment: the control lane may start the next one
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_sd);
+        worker_sync();                                               // nobody zeroes the patch while a slower warp still reads the tile
+        tick(7);
+        if (prof) pc[10] += 1;
+    }
+    }
+    if (prof) {
+        pc[11] = (unsigned long long)(clock64() - t_start);
+        for (int i = 0; i < 12; ++i) p.prof[i] = pc[i];
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (is_ctl) tmem_dealloc(tmem_base, 512);
 }
 
 namespace {
@@ -483,19 +673,51 @@ constexpr size_t MB_SMEM_MAX = 224 * 1024;      // dynamic part: the 227 KB per-
 
 struct MbVariant { int k, g, xb, yb; };
 
-// the pixel block and channel group this build instantiates for a layer shape (stride 1 only), or g = 0
+// the channel group and pixel block this build instantiates for a layer shape (stride 1 only), or g = 0:
+// 384 worker threads = G/2 channel pairs x block slots, every block slot used when the image has exactly that many blocks
 MbVariant mb_pick(int h, int w, int k) {
-    if ((k != 3 && k != 5) || w % 2 || h % 3) return MbVariant{0, 0, 0, 0};
-    const int nblk = (h / 3) * (w / 2);              // 2 x 3 output blocks
-    if (nblk <= 16) return MbVariant{k, 64, 2, 3};   // 32 channel pairs x 16 block slots
-    if (nblk <= 32) return MbVariant{k, 32, 2, 3};   // 16 channel pairs x 32 block slots
-    return MbVariant{0, 0, 0, 0};
+    if (k != 3 && k != 5) return MbVariant{0, 0, 0, 0};
+    const int cand[4][3] = {{32, 4, 2}, {64, 4, 1}, {32, 2, 2}, {64, 2, 1}};     // G, XB, YB
+    int best = -1;
+    double best_u = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        const int g = cand[i][0], xb = cand[i][1], yb = cand[i][2];
+        if (w % xb || h % yb) continue;
+        const int slots = MB_THREADS / (g / 2), nblk = (h / yb) * (w / xb);
+        if (nblk > slots) continue;
+        const double u = (double)nblk / slots * (xb * yb >= 8 ? 1.0 : 0.8);        // larger blocks reuse more of each patch read
+        if (u > best_u) { best_u = u; best = i; }
+    }
+    if (best < 0) return MbVariant{0, 0, 0, 0};
+    return MbVariant{k, cand[best][0], cand[best][1], cand[best][2]};
 }
 
-template <int K, int G>
-cudaError_t mb_launch_kg(const MbconvParams& p, int grid, size_t smem, cudaStream_t stream) {
-    k_mbconv<K, G, 2, 3><<<grid, MB_THREADS, smem, stream>>>(p);
+template <int K, int G, int XB, int YB>
+cudaError_t mb_launch_v(const MbconvParams& p, int grid, size_t smem, cudaStream_t stream) {
+    if (p.cout * 8 <= 3 * MB_THREADS) k_mbconv<K, G, XB, YB, 3><<<grid, MB_BLOCK, smem, stream>>>(p);
+    else k_mbconv<K, G, XB, YB, 6><<<grid, MB_BLOCK, smem, stream>>>(p);
     return cudaGetLastError();
+}
+template <int K, int G, int XB, int YB>
+cudaError_t mb_attr_v() {
+    cudaError_t e = cudaFuncSetAttribute(k_mbconv<K, G, XB, YB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mbconv<K, G, XB, YB, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM_MAX);
+    return e;
+}
+template <int K>
+cudaError_t mb_attr_k() {
+    cudaError_t e = mb_attr_v<K, 32, 4, 2>();
+    if (e == cudaSuccess) e = mb_attr_v<K, 64, 4, 1>();
+    if (e == cudaSuccess) e = mb_attr_v<K, 32, 2, 2>();
+    if (e == cudaSuccess) e = mb_attr_v<K, 64, 2, 1>();
+    return e;
+}
+template <int K>
+cudaError_t mb_launch_k(const MbVariant& v, const MbconvParams& p, int grid, size_t smem, cudaStream_t stream) {
+    if (v.g == 32 && v.xb == 4) return mb_launch_v<K, 32, 4, 2>(p, grid, smem, stream);
+    if (v.g == 64 && v.xb == 4) return mb_launch_v<K, 64, 4, 1>(p, grid, smem, stream);
+    if (v.g == 32) return mb_launch_v<K, 32, 2, 2>(p, grid, smem, stream);
+    return mb_launch_v<K, 64, 2, 1>(p, grid, smem, stream);
 }
 
 }  // namespace
@@ -504,9 +726,13 @@ int mbconv_group(int h, int w, int k) { return mb_pick(h, w, k).g; }
 
 bool mbconv_supported(int h, int w, int k, int stride, int cin, int cexp, int cout, int r) {
     if (stride != 1) return false;
+    // one segment per CTA pass: images under 128 pixels leave most of the 128-row MMA tile, the FCs and the per-chunk
+    // weight images unamortised (measured on 3x16: 0.27 ms fused vs 0.16 ms layer by layer) - those blocks stay layered
+    static const bool small_ok = [] { const char* ev = getenv("BN_MBCONV_SMALL"); return ev && ev[0] == '1'; }();
+    if (h * w < 128 && !small_ok) return false;
     const MbVariant v = mb_pick(h, w, k);
     if (v.g == 0) return false;
-    if ((cin & 7) || (cexp % v.g) || (cout & 15) || cout > 256 || r < 1 || r > 256) return false;
+    if ((cin & 7) || (cexp % v.g) || (cout & 15) || cout * 8 > 6 * MB_THREADS || r < 1 || r > 256) return false;
     const MbLayout L = mb_layout(h, w, k, cin, cexp, cout, r, v.g);
     if (L.total > MB_SMEM_MAX) return false;
     if ((uint32_t)L.n_mt * 2u * (uint32_t)v.g * 2u > 512u) return false;     // two E buffers in TMEM
@@ -515,10 +741,8 @@ bool mbconv_supported(int h, int w, int k, int stride, int cin, int cexp, int co
 }
 
 cudaError_t mbconv_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(k_mbconv<3, 32, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM_MAX);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mbconv<5, 32, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM_MAX);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mbconv<3, 64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM_MAX);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mbconv<5, 64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MB_SMEM_MAX);
+    cudaError_t e = mb_attr_k<3>();
+    if (e == cudaSuccess) e = mb_attr_k<5>();
     return e;
 }
 
@@ -528,10 +752,8 @@ cudaError_t launch_mbconv(const MbconvParams& p, int num_sms, cudaStream_t strea
     const MbVariant v = mb_pick(p.h, p.w, p.k);
     const MbLayout L = mb_layout(p.h, p.w, p.k, p.cin, p.cexp, p.cout, p.r, v.g);
     const int grid = p.batch < num_sms ? p.batch : num_sms;
-    if (v.k == 3 && v.g == 32) return mb_launch_kg<3, 32>(p, grid, L.total, stream);
-    if (v.k == 5 && v.g == 32) return mb_launch_kg<5, 32>(p, grid, L.total, stream);
-    if (v.k == 3 && v.g == 64) return mb_launch_kg<3, 64>(p, grid, L.total, stream);
-    return mb_launch_kg<5, 64>(p, grid, L.total, stream);
+    if (v.k == 3) return mb_launch_k<3>(v, p, grid, L.total, stream);
+    return mb_launch_k<5>(v, p, grid, L.total, stream);
 }
 
 }  // namespace bn

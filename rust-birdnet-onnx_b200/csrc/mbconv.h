@@ -29,12 +29,14 @@ struct MbconvParams {
     __half* out_hi;           // block output planes [batch][npix][cout]
     size_t out_plane;
     int batch, h, w, k, cin, cexp, cout, r, ldw1, ldw2;
+    unsigned long long* prof; // optional [12] phase cycle counters of CTA 0 (development aid), or nullptr
+    int debug;                // development experiments (BN_MB_DEBUG bits: skip parts of the work to time the rest), 0 in production
 };
 
 struct MbLayout {
-    int n_box, n_mt, kc_e, kc_p, npixp;
-    uint32_t xa_bytes, we_stage, da_stage, wp_stage, patch_bytes;
-    uint32_t off_xa, off_we, off_da, off_wp, off_patch, off_part, off_pool, off_gate, off_r, off_fc, total;
+    int n_box, n_mt, kc_e, kc_p, npixp, n_da;
+    uint32_t xa_bytes, we_stage, da_stage, wp_stage, patch_bytes, stg_pitch;
+    uint32_t off_xa, off_we, off_da, off_wp, off_patch, off_wd, off_part, off_pool, off_gate, off_r, off_fc, total;
 };
 
 cudaError_t mbconv_init_device();

@@ -111,7 +111,8 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
     const bool w_res = MODE == TC_IN_TMA && p.w_resident != 0;        // weights of this CTA's n tile resident, ring = A tiles only
     const uint32_t stage_bytes = 2u * A_TILE_BYTES + (w_res ? 0u : w_bytes);
     const int total_tiles = p.m_tiles * p.n_tiles;
-    uint8_t* tiles0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer arithmetic on the shared array (a uintptr_t round trip loses the address space: generic LD / ST)
+    uint8_t* tiles0 = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     uint8_t* tiles = tiles0 + (w_res ? (size_t)p.k_chunks * w_bytes : 0);     // ring base (resident weights, if any, sit in front of it)
 
     if (tid == 0) {
