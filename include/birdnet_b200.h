@@ -121,6 +121,10 @@ void bn_engine_destroy(bn_engine* engine);
 int bn_engine_io_info(const bn_engine* engine, bn_io_info* out);
 int bn_model_inspect(const char* onnx_path, int32_t model_type_override, bn_io_info* out);
 /* detect_model_type on explicit shapes (src/detection.rs:15-80); shapes are rank-prefixed rows */
+/* Canonical text of the layer plan the file is matched into (front-end constants, one line per fused op with shapes,
+ * activation, gate / residual flags and a hash of the weight bits; value names left out): two files describing the same
+ * network give the same text whichever exporter wrote them.  buf may be NULL to query `needed` (bytes incl. NUL). */
+int bn_model_plan_summary(const char* onnx_path, int32_t model_type_override, char* buf, uint64_t cap, uint64_t* needed);
 int bn_detect_model_type(const int64_t* input_dims, int32_t input_rank, const int64_t* output_dims,
                          const int32_t* output_ranks, int32_t n_outputs, int32_t model_type_override,
                          bn_io_info* out);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "bn_engine_destroy": (None, [_vp]),
     "bn_engine_io_info": (C.c_int, [_vp, _P(IoInfo)]),
     "bn_model_inspect": (C.c_int, [C.c_char_p, C.c_int32, _P(IoInfo)]),
+    "bn_model_plan_summary": (C.c_int, [C.c_char_p, C.c_int32, C.c_char_p, C.c_uint64, _P(C.c_uint64)]),
     "bn_detect_model_type": (C.c_int, [_P(C.c_int64), C.c_int32, _P(C.c_int64), _P(C.c_int32),
                                        C.c_int32, C.c_int32, _P(IoInfo)]),
     "bn_engine_set_postprocess": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.c_float]),

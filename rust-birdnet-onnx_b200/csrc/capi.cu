@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/birdnet_b200.h.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "engine.h"
@@ -54,6 +55,53 @@ int bn_model_inspect(const char* onnx_path, int32_t model_type_override, bn_io_i
     int st = load_plan(onnx_path, model_type_override, plan);
     if (st != BN_OK) return st;
     return fill_io_info(plan, out);
+}
+
+// Canonical text form of the layer plan a file is matched into: value names are left out, weights enter through a
+// hash of their bits, so two files that describe the same network (whoever wrote them) give the same text.
+static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+int bn_model_plan_summary(const char* onnx_path, int32_t model_type_override, char* buf, uint64_t cap, uint64_t* needed) {
+    Plan plan;
+    int st = load_plan(onnx_path, model_type_override, plan);
+    if (st != BN_OK) return st;
+    std::string out;
+    char line[512];
+    const FrontEndPlan& fe = plan.fe;
+    snprintf(line, sizeof line, "frontend kind=%d samples=%d pad_end=%d normalize=%d eps=%.9g half=%.9g two=%.9g log_floor=%.9g log_scale=%.9g\n",
+             fe.kind, fe.sample_count, fe.pad_end, (int)fe.normalize, fe.eps, fe.half, fe.two, fe.log_floor, fe.log_scale);
+    out += line;
+    for (auto& b : fe.branches) {
+        snprintf(line, sizeof line, "  branch n_fft=%d hop=%d bins=%d mels=%d frames=%d exponent=%.9g flip=%d window=%016llx mel=%016llx\n",
+                 b.n_fft, b.hop, b.n_bins, b.n_mels, b.n_frames, b.exponent, (int)b.flip,
+                 (unsigned long long)fnv1a(b.window.data(), b.window.size() * 4), (unsigned long long)fnv1a(b.mel.data(), b.mel.size() * 4));
+        out += line;
+    }
+    for (auto& op : plan.ops) {
+        // weights hashed in a layout-independent order: the engine layout is [k*k*cin][ldw] with pad columns
+        uint64_t hw = 1469598103934665603ull;
+        if (op.kind == OP_DWCONV) hw = fnv1a(op.weight.data(), op.weight.size() * 4);
+        else if (op.kind != OP_GAP) {
+            const size_t rows = op.weight.size() / (size_t)std::max(op.ldw, 1);
+            for (size_t r = 0; r < rows; ++r) hw = fnv1a(op.weight.data() + r * op.ldw, (size_t)op.cout * 4, hw);
+        }
+        snprintf(line, sizeof line, "op kind=%d k=%d s=%d p=%d cin=%d cout=%d in=%dx%d out=%dx%d act=%d gated=%d residual=%d w=%016llx b=%016llx\n",
+                 op.kind, op.k, op.stride, op.pad, op.cin, op.cout, op.hin, op.win, op.hout, op.wout, op.act, (int)(op.in_scale >= 0),
+                 (int)(op.residual >= 0), (unsigned long long)hw, (unsigned long long)fnv1a(op.bias.data(), op.bias.size() * 4));
+        out += line;
+    }
+    snprintf(line, sizeof line, "outputs=%zu model_type=%d num_species=%d embedding_dim=%d\n", plan.outputs.size(), plan.model_type, plan.num_species, plan.embedding_dim);
+    out += line;
+    if (needed) *needed = out.size() + 1;
+    if (buf && cap) {
+        const size_t n = std::min<size_t>(out.size(), (size_t)cap - 1);
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return BN_OK;
 }
 
 int bn_detect_model_type(const int64_t* input_dims, int32_t input_rank, const int64_t* output_dims,

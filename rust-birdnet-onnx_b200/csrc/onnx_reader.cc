@@ -2,6 +2,7 @@
 #include "onnx_reader.h"
 
 #include <cerrno>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -141,6 +142,11 @@ void parse_attr(const uint8_t* p, size_t n, OnnxAttr& a) {
             case 2: a.f = f32_of(f); break;
             case 3: a.i = (int64_t)varint_of(f); break;
             case 4: a.s = str(f); break;
+            case 5:                                   // t: TensorProto (Constant nodes of exporters that do not use initializers)
+                if (f.wt != 2) throw std::runtime_error("onnx: tensor attribute has wire type " + std::to_string(f.wt));
+                parse_tensor(f.data, f.len, a.t);
+                a.has_t = true;
+                break;
             case 7: packed_floats(f, a.floats); break;
             case 8: packed_ints(f, a.ints); break;
             default: break;
@@ -218,6 +224,104 @@ void parse_graph(const uint8_t* p, size_t n, OnnxModel& m) {
     }
 }
 
+// Shape arithmetic that exporters leave in the graph (torch lowers F.pad's amounts to ConstantOfShape / Concat / Reshape /
+// Slice / Transpose / Cast over tiny int64 tensors): nodes of that vocabulary whose inputs are all constants are evaluated
+// here and become initializers, as ONNX Runtime's constant folding does.  Tensors of rank <= 2 and <= 64 elements only.
+struct SmallI64 { std::vector<int64_t> dims, v; };
+bool small_i64(const OnnxModel& m, const std::string& name, SmallI64& out) {
+    const OnnxTensor* t = m.init(name);
+    if (!t || t->data_type != 7 || t->dims.size() > 2 || t->numel() > 64) return false;
+    out.dims = t->dims;
+    out.v.resize(t->numel());
+    for (size_t i = 0; i < out.v.size(); ++i) out.v[i] = t->i64(i);
+    return true;
+}
+void fold_int64_constants(OnnxModel& m) {
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (size_t n = 0; n < m.nodes.size(); ++n) {
+            const OnnxNode& nd = m.nodes[n];
+            if (nd.outputs.size() != 1) continue;
+            SmallI64 r;
+            bool ok = false;
+            if (nd.op == "ConstantOfShape" && nd.inputs.size() == 1) {
+                SmallI64 sh;
+                const OnnxAttr* v = nd.attr("value");
+                if (small_i64(m, nd.inputs[0], sh) && sh.dims.size() <= 1 && sh.v.size() <= 2 && v && v->has_t && v->t.data_type == 7 && v->t.numel() == 1) {
+                    size_t cnt = 1;
+                    for (auto d : sh.v) { if (d < 0 || d > 64) { cnt = 0; break; } cnt *= (size_t)d; }
+                    if (cnt <= 64) { r.dims = sh.v; r.v.assign(cnt, v->t.i64(0)); ok = true; }
+                }
+            } else if (nd.op == "Concat" && nd.attr_i("axis", 0) == 0 && !nd.inputs.empty()) {
+                ok = true;
+                for (auto& in : nd.inputs) {
+                    SmallI64 a;
+                    if (!small_i64(m, in, a) || a.dims.size() > 1) { ok = false; break; }
+                    r.v.insert(r.v.end(), a.v.begin(), a.v.end());
+                }
+                r.dims = {(int64_t)r.v.size()};
+            } else if (nd.op == "Reshape" && nd.inputs.size() == 2) {
+                SmallI64 a, sh;
+                if (small_i64(m, nd.inputs[0], a) && small_i64(m, nd.inputs[1], sh) && sh.dims.size() <= 1 && sh.v.size() <= 2) {
+                    int64_t known = 1, infer = -1;
+                    for (size_t i = 0; i < sh.v.size(); ++i) { if (sh.v[i] == -1) infer = (int64_t)i; else known *= sh.v[i]; }
+                    r.dims = sh.v;
+                    if (infer >= 0 && known > 0) r.dims[infer] = (int64_t)a.v.size() / known;
+                    int64_t tot = 1;
+                    for (auto d : r.dims) tot *= d;
+                    if (tot == (int64_t)a.v.size()) { r.v = a.v; ok = true; }
+                }
+            } else if (nd.op == "Transpose") {
+                SmallI64 a;
+                const OnnxAttr* pm = nd.attr("perm");
+                if (small_i64(m, nd.inputs[0], a) && a.dims.size() == 2 && pm && pm->ints == std::vector<int64_t>{1, 0}) {
+                    const int64_t R = a.dims[0], Cc = a.dims[1];
+                    r.dims = {Cc, R};
+                    r.v.resize(a.v.size());
+                    for (int64_t i = 0; i < R; ++i) for (int64_t j = 0; j < Cc; ++j) r.v[j * R + i] = a.v[i * Cc + j];
+                    ok = true;
+                }
+            } else if (nd.op == "Slice" && nd.inputs.size() >= 3) {
+                SmallI64 a, st, en, ax, sp;
+                if (small_i64(m, nd.inputs[0], a) && a.dims.size() >= 1 && small_i64(m, nd.inputs[1], st) && small_i64(m, nd.inputs[2], en) &&
+                    st.v.size() == 1 && en.v.size() == 1) {
+                    int64_t axis = 0, step = 1;
+                    if (nd.inputs.size() >= 4 && !nd.inputs[3].empty()) { if (!small_i64(m, nd.inputs[3], ax) || ax.v.size() != 1) continue; axis = ax.v[0]; }
+                    if (nd.inputs.size() >= 5 && !nd.inputs[4].empty()) { if (!small_i64(m, nd.inputs[4], sp) || sp.v.size() != 1) continue; step = sp.v[0]; }
+                    if (axis < 0) axis += (int64_t)a.dims.size();
+                    if (axis == 0 && (step == 1 || step == -1)) {
+                        const int64_t R = a.dims[0], Cc = a.dims.size() == 2 ? a.dims[1] : 1;
+                        auto clampi = [&](int64_t x, int64_t lo, int64_t hi) { return x < lo ? lo : (x > hi ? hi : x); };
+                        int64_t s0 = st.v[0], e0 = en.v[0];
+                        if (s0 < 0) s0 += R;
+                        if (e0 < 0 && e0 > INT64_MIN / 2) e0 += R;
+                        std::vector<int64_t> rows;
+                        if (step == 1) { s0 = clampi(s0, 0, R); e0 = clampi(e0, 0, R); for (int64_t i = s0; i < e0; ++i) rows.push_back(i); }
+                        else { s0 = clampi(s0, -1, R - 1); e0 = clampi(e0, -1, R - 1); for (int64_t i = s0; i > e0; --i) rows.push_back(i); }
+                        for (auto i : rows) r.v.insert(r.v.end(), a.v.begin() + i * Cc, a.v.begin() + (i + 1) * Cc);
+                        r.dims = a.dims;
+                        r.dims[0] = (int64_t)rows.size();
+                        ok = true;
+                    }
+                }
+            } else if (nd.op == "Cast" && nd.attr_i("to", 0) == 7) {
+                ok = small_i64(m, nd.inputs[0], r);
+            }
+            if (!ok) continue;
+            OnnxTensor t;
+            t.name = nd.outputs[0];
+            t.data_type = 7;
+            t.dims = r.dims;
+            t.i64_fallback = r.v;
+            m.initializers[t.name] = std::move(t);
+            m.nodes.erase(m.nodes.begin() + (long)n);
+            changed = true;
+            break;
+        }
+    }
+}
+
 }  // namespace
 
 int64_t OnnxTensor::i64(size_t i) const {
@@ -259,6 +363,30 @@ void parse_onnx(OnnxModel& m) {
         }
     }
     if (!have_graph) throw std::runtime_error("onnx: no graph in model file");
+    // Constant nodes (torch's exporter emits scalars and small tables this way) become initializers under their output
+    // name, so the planner sees one dialect: constants are always initializers
+    {
+        std::vector<OnnxNode> kept;
+        kept.reserve(m.nodes.size());
+        for (auto& nd : m.nodes) {
+            if (nd.op == "Constant" && nd.outputs.size() == 1) {
+                const OnnxAttr* v = nd.attr("value");
+                OnnxTensor t;
+                if (v && v->has_t) t = v->t;
+                else if (const OnnxAttr* vf = nd.attr("value_float")) { t.data_type = 1; t.f32_fallback = {vf->f}; }
+                else if (const OnnxAttr* vi = nd.attr("value_int")) { t.data_type = 7; t.i64_fallback = {vi->i}; }
+                else if (const OnnxAttr* vfs = nd.attr("value_floats")) { t.data_type = 1; t.f32_fallback = vfs->floats; t.dims = {(int64_t)vfs->floats.size()}; }
+                else if (const OnnxAttr* vis = nd.attr("value_ints")) { t.data_type = 7; t.i64_fallback = vis->ints; t.dims = {(int64_t)vis->ints.size()}; }
+                else throw std::runtime_error("onnx: Constant node '" + nd.name + "' has no supported value attribute");
+                t.name = nd.outputs[0];
+                m.initializers[t.name] = std::move(t);
+                continue;
+            }
+            kept.push_back(std::move(nd));
+        }
+        m.nodes.swap(kept);
+    }
+    fold_int64_constants(m);
     // initializers that are also listed as graph inputs (older exporters) are not real inputs
     std::vector<OnnxValueInfo> real;
     for (auto& vi : m.inputs)

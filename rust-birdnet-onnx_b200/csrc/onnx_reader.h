@@ -39,6 +39,8 @@ struct OnnxAttr {
     std::string s;
     std::vector<int64_t> ints;
     std::vector<float> floats;
+    bool has_t = false;
+    OnnxTensor t;                   // TENSOR attribute (Constant nodes)
 };
 
 struct OnnxNode {

@@ -67,8 +67,31 @@ struct Matcher {
         br.n_bins = br.n_fft / 2 + 1;
         consumed[stft_idx] = true;
 
+        // torch's exporter keeps torch.stft's [B, bins, frames, 2] layout: Transpose(0,2,1,3) in front of the gathers and
+        // Transpose(0,2,1) behind each of them; the pair cancels (the in-house writer emits neither)
+        std::string stft_out = st.outputs[0];
+        bool swapped = false;
+        {
+            const int t = sole_consumer(stft_out);
+            if (t >= 0 && m.nodes[t].op == "Transpose") {
+                const OnnxAttr* pm = m.nodes[t].attr("perm");
+                if (!pm || pm->ints != std::vector<int64_t>{0, 2, 1, 3}) fail("STFT output: only Transpose(0,2,1,3) is understood");
+                consumed[t] = true;
+                stft_out = m.nodes[t].outputs[0];
+                swapped = true;
+            }
+        }
+        auto unswap = [&](std::string& v) {
+            if (!swapped || v.empty()) return;
+            const int t = sole_consumer(v);
+            const OnnxAttr* pm = t >= 0 ? m.nodes[t].attr("perm") : nullptr;
+            if (t < 0 || m.nodes[t].op != "Transpose" || !pm || pm->ints != std::vector<int64_t>{0, 2, 1})
+                fail("STFT output: expected Transpose(0,2,1) behind the real / imaginary Gather");
+            consumed[t] = true;
+            v = m.nodes[t].outputs[0];
+        };
         // real / imag gathers
-        auto& cons = consumers[st.outputs[0]];
+        auto& cons = consumers[stft_out];
         std::string re, im;
         for (int ci : cons) {
             const OnnxNode& g = m.nodes[ci];
@@ -78,6 +101,8 @@ struct Matcher {
             consumed[ci] = true;
         }
         if (re.empty()) fail("STFT real part is unused");
+        unswap(re);
+        unswap(im);
         std::string cur;
         if (im.empty()) {
             is_logmel = false;
@@ -201,9 +226,11 @@ struct Matcher {
             cur = m.nodes[n0].outputs[0];
             n0 = sole_consumer(cur);
         }
-        if (n0 < 0 || m.nodes[n0].op != "Unsqueeze") fail("front-end: expected Unsqueeze of the signal to [B,S,1]");
-        consumed[n0] = true;
-        cur = m.nodes[n0].outputs[0];
+        // ONNX STFT takes [B,S,1]; torch's exporter feeds the [B,S] signal directly (ONNX Runtime accepts both)
+        if (n0 >= 0 && m.nodes[n0].op == "Unsqueeze") {
+            consumed[n0] = true;
+            cur = m.nodes[n0].outputs[0];
+        }
 
         std::vector<std::string> branch_out;
         bool any_logmel = false;
@@ -249,7 +276,12 @@ struct Matcher {
             consumed[n] = true;
             if (nd.op == "Conv") match_conv((int)n);
             else if (nd.op == "Gemm") match_gemm((int)n);
-            else if (nd.op == "GlobalAveragePool") {
+            else if (nd.op == "GlobalAveragePool" || nd.op == "ReduceMean") {
+                if (nd.op == "ReduceMean") {             // torch: x.mean(dim=(2,3), keepdim=True)
+                    const OnnxAttr* ax = nd.attr("axes");
+                    if (!ax || ax->ints != std::vector<int64_t>{2, 3} || nd.attr_i("keepdims", 1) != 1)
+                        fail("ReduceMean must average axes (2,3) with keepdims=1 (a global average pool)");
+                }
                 int in = resolve_plain(nd.inputs[0], "GlobalAveragePool");
                 PlanOp op;
                 op.kind = OP_GAP; op.name = nd.name; op.in = in;

@@ -76,10 +76,13 @@ class SpecModule(nn.Module):
         st = st.transpose(1, 2)
         mag = torch.sqrt(st[..., 0] * st[..., 0] + st[..., 1] * st[..., 1])
         m = mag @ self.mel0
-        return (torch.log(m + fe.log_floor) * fe.log_scale).unsqueeze(1)
+        return torch.log(m + fe.log_floor) * fe.log_scale           # [B, frames, mels]
 
     def forward(self, x):
-        t = {"spec": self.frontend(x)}
+        f = self.frontend(x)
+        t = {"spec": f}
+        if self.spec.frontend.kind != "birdnet_v24":
+            t = {"spectrogram": f, "spec": f.unsqueeze(1)}
         for op in self.spec.ops:
             k = op["op"]
             if k == "conv":
