@@ -258,7 +258,7 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
         if (tc_enabled && !no_mbconv && e->dev_ops[i].use_tc && match_mbconv(p, i)) {
             DevOp& d = e->dev_ops[i];
             const PlanOp &dw = p.ops[i + 1], &pr = p.ops[i + 5];
-            d.mb_group = mbconv_group(dw.hin, dw.win, dw.k);
+            d.mb_group = mbconv_group(dw.hin, dw.win, dw.k, op.cin, op.cout, pr.cout, p.ops[i + 3].cout);
             std::vector<uint16_t> pack;
             int nt_ = 0, kc_ = 0;
             tc_pack_weights(op.weight.data(), op.cin, op.cout, op.ldw, d.mb_group, pack, &nt_, &kc_);
@@ -269,6 +269,10 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
                 for (int n = 0; n < pr.cout; ++n) wt[(size_t)n * pr.cin + c] = pr.weight[(size_t)c * pr.ldw + n];
             BN_CUDA(cudaMalloc(&d.mb_wpT, wt.size() * sizeof(float)));
             BN_CUDA(cudaMemcpy(d.mb_wpT, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+            std::vector<uint16_t> ppack;                      // one N tile = all output channels: [k_chunk][hi|lo][cout x 64]
+            tc_pack_weights(pr.weight.data(), pr.cin, pr.cout, pr.ldw, pr.cout, ppack, &nt_, &kc_);
+            BN_CUDA(cudaMalloc(&d.mb_wp_pack, ppack.size() * sizeof(uint16_t)));
+            BN_CUDA(cudaMemcpy(d.mb_wp_pack, ppack.data(), ppack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         }
         std::vector<float>().swap(op.weight);   // host copy no longer needed
     }
@@ -364,6 +368,7 @@ bn_engine::~bn_engine() {
         if (d.bias) cudaFree(d.bias);
         if (d.wpack) cudaFree(d.wpack);
         if (d.mb_we_pack) cudaFree(d.mb_we_pack);
+        if (d.mb_wp_pack) cudaFree(d.mb_wp_pack);
         if (d.mb_wpT) cudaFree(d.mb_wpT);
     }
     for (auto* b : d_basis) cudaFree(b);
@@ -623,7 +628,7 @@ static int enqueue_ops_tc(bn_ctx* c, int B, uint64_t& launches) {
                 mp.wd = e->dev_ops[i + 1].weight; mp.bd = e->dev_ops[i + 1].bias;
                 mp.w1 = e->dev_ops[i + 3].weight; mp.b1 = e->dev_ops[i + 3].bias; mp.ldw1 = f1.ldw;
                 mp.w2 = e->dev_ops[i + 4].weight; mp.b2 = e->dev_ops[i + 4].bias; mp.ldw2 = f2.ldw;
-                mp.wpT = d.mb_wpT; mp.bp = e->dev_ops[i + 5].bias;
+                mp.wp_pack = d.mb_wp_pack; mp.wpT = d.mb_wpT; mp.bp = e->dev_ops[i + 5].bias;
                 mp.d_hi = dp.hi; mp.d_plane = dp.plane;
                 if (pr.residual >= 0) { const PlanesPtr rp = planes_of(c, pr.residual); mp.res_hi = rp.hi; mp.res_plane = rp.plane; }
                 const PlanesPtr op_ = planes_of(c, pr.out);

@@ -45,7 +45,8 @@ struct DevOp {
     // fused MBConv block starting at this (expand) op: expand -> depthwise -> pool -> FC -> FC -> projection = ops i .. i+5
     int mb_group = 0;            // channel group of the fused kernel (0: block runs layer by layer)
     void* mb_we_pack = nullptr;  // expand weights packed with N tile = mb_group
-    float* mb_wpT = nullptr;     // projection weights [cout][cexp]
+    void* mb_wp_pack = nullptr;  // projection weights packed with one N tile = cout
+    float* mb_wpT = nullptr;     // projection weights [cout][cexp] FP32
 };
 
 struct RangeDev {   // dense per-class tri-state on the device

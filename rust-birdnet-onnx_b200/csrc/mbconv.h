@@ -20,7 +20,8 @@ struct MbconvParams {
     const float* b1;          // [r]
     const float* w2;          // [r][ldw2] squeeze-excite expand (cexp outputs)
     const float* b2;          // [cexp]
-    const float* wpT;         // [cout][cexp] projection weights, output-channel major
+    const void* wp_pack;      // projection weights, tc_pack_weights(nt = cout): [k_chunk][hi|lo][cout x 64] fp16 (gate applied to D)
+    const float* wpT;         // projection weights [cout][cexp] FP32, output-channel major (gate applied to the weights)
     const float* bp;          // [cout]
     __half* d_hi;             // D planes (un-gated), lo = d_hi + d_plane
     size_t d_plane;
@@ -29,6 +30,7 @@ struct MbconvParams {
     __half* out_hi;           // block output planes [batch][npix][cout]
     size_t out_plane;
     int batch, h, w, k, cin, cexp, cout, r, ldw1, ldw2;
+    int segs;                 // segments per CTA pass (set by launch_mbconv)
     unsigned long long* prof; // optional [12] phase cycle counters of CTA 0 (development aid), or nullptr
     int debug;                // development experiments (BN_MB_DEBUG bits: skip parts of the work to time the rest), 0 in production
 };
@@ -43,7 +45,7 @@ cudaError_t mbconv_init_device();
 // stride-1 MBConv block with squeeze-excite this build has a fused kernel for?
 bool mbconv_supported(int h, int w, int k, int stride, int cin, int cexp, int cout, int r);
 // channel group size the kernel uses for this shape (the N tile the expand weights must be packed with), 0 = unsupported
-int mbconv_group(int h, int w, int k);
+int mbconv_group(int h, int w, int k, int cin, int cexp, int cout, int r);
 cudaError_t launch_mbconv(const MbconvParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace bn
