@@ -70,7 +70,8 @@ def _peaks():
         with open(p) as f:
             d = json.load(f)
         return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
-                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), sm_hz=float(d.get("sm_max_mhz", 1965.0)) * 1e6,
+                    src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
@@ -298,11 +299,29 @@ def _stage_roofline(spec, stage_times, batch, peaks):
             blk = name[:-len(".mbconv")]
             parts = [rows[k] for k in (blk + ".expand", blk + ".dw", blk + ".project") if k in rows]
             if len(parts) == 3:
+                # Four ceilings for a fused block; the one that takes longest at peak is its roofline:
+                #   HBM     block input read once + block output written once (+ weights)
+                #   tensor  expand + projection FLOPs at the sustained dense rate
+                #   FP32    depthwise MACs on the CUDA cores: 128 FMA lanes x SMs x clock
+                #   MUFU    two SiLUs per expanded element (ex2 + rcp each): 16 special-function lanes x SMs x clock
                 byts = 4.0 * ((parts[0]["in_elems"] + parts[2]["out_elems"]) * batch + sum(r["w_elems"] for r in parts))
-                flops = 2.0 * sum(r["macs"] for r in parts) * batch
-                d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
-                         alg_per_segment=4 * (parts[0]["in_elems"] + parts[2]["out_elems"]),
-                         tensor_tflops=flops / (ms * 1e-3) / 1e12)
+                tflops = 2.0 * (parts[0]["macs"] + parts[2]["macs"]) * batch
+                fma = float(parts[1]["macs"]) * batch
+                mufu = 2.0 * (parts[0]["out_elems"] + parts[1]["out_elems"]) * batch
+                clk = peaks.get("sm_hz", 1.965e9)
+                t = {"hbm": byts / (peaks["hbm"] * 1e9), "tensor": tflops / (peaks["tf_sust"] * 1e12),
+                     "fp32-fma": fma / (148 * 128 * clk), "mufu": mufu / (148 * 16 * clk)}
+                b = max(t, key=t.get)
+                if b == "hbm":
+                    d.update(bound="hbm", achieved=byts / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
+                elif b == "tensor":
+                    d.update(bound="tensor", achieved=tflops / (ms * 1e-3) / 1e12, peak=peaks["tf_sust"], unit="TFLOP/s")
+                elif b == "fp32-fma":
+                    d.update(bound="fp32-fma", achieved=fma / (ms * 1e-3) / 1e12, peak=148 * 128 * clk / 1e12, unit="TFMA/s")
+                else:
+                    d.update(bound="mufu", achieved=mufu / (ms * 1e-3) / 1e12, peak=148 * 16 * clk / 1e12, unit="Tops/s")
+                d.update(alg_per_segment=4 * (parts[0]["in_elems"] + parts[2]["out_elems"]),
+                         ceilings_ms={k: round(v * 1e3, 5) for k, v in t.items()})
             else:
                 continue
         elif base in rows:
@@ -349,9 +368,11 @@ def _stage_roofline(spec, stage_times, batch, peaks):
     return dom, out
 
 
-def _pinned_copy_rates(torch, device, in_bytes, out_bytes, reps=10):
+def _pinned_copy_rates(torch, device, in_bytes, out_bytes, reps=10, barrier=None):
     """Live staging roofline: pinned cudaMemcpyAsync H2D / D2H rates (GB/s) of batch-sized buffers on this GPU, CUDA
-    events on the copy stream (tools/pcie_bench.cu is the multi-GPU version of the same measurement)."""
+    events on the copy stream.  With several ranks every rank copies at the same time (barrier first), so the figure is
+    this GPU's share of the box's host-to-device fabric, not the rate of a GPU copying alone (tools/pcie_bench.cu:
+    55.5 GB/s alone, 23-35 GB/s each when eight GPUs copy together)."""
     h_in = torch.empty(in_bytes, dtype=torch.uint8).pin_memory()
     h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
     d_in = torch.empty(in_bytes, dtype=torch.uint8, device=device)
@@ -362,6 +383,9 @@ def _pinned_copy_rates(torch, device, in_bytes, out_bytes, reps=10):
         for src, dst, n in ((h_in, d_in, in_bytes), (d_out, h_out, out_bytes)):
             for _ in range(2):
                 dst.copy_(src, non_blocking=True)
+            st.synchronize()
+            if barrier is not None:
+                barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
             for _ in range(reps):
@@ -590,6 +614,14 @@ def run_ours(args):
                   "segments": world * sum(got), "api": "Classifier.predict_pcm16_stream -> bn_ctx_run_pcm16 "
                   "(16-bit PCM in, conversion + chunking on the device; not the reference's f32-slice API)"}
 
+    # ---- staging roofline: every rank copies at the same time -> this GPU's share of the box's host-to-device fabric ----
+    h2d_gbs, d2h_gbs = _pinned_copy_rates(torch, torch.device("cuda", local), h2d, max(d2h, 1 << 20), barrier=barrier)
+    h2d_box = h2d_gbs
+    if dist is not None:
+        t = torch.tensor([h2d_gbs], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d_box = float(t.item())
+
     # ---- roofline of the dominant kernel, timed live with CUDA events on the engine's stream ----
     roof, stages, classes = None, [], []
     if rank == 0:
@@ -612,13 +644,12 @@ def run_ours(args):
         classes = [{"class": k, "ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4), "stages": v["stages"]}
                    for k, v in sorted(by_class.items(), key=lambda kv: -kv[1]["ms"])]
         # staging over PCIe: what the end-to-end API moved per second against the pinned-copy rate measured live
-        h2d_gbs, d2h_gbs = _pinned_copy_rates(torch, torch.device("cuda", local), h2d, max(d2h, 1 << 20))
-        moved = e2e_value / max(world, 1) * (h2d + d2h) / B / 1e9          # GB/s through this GPU's link
-        stages.append({"stage": "staging (H2D of the segments + D2H of the results, per GPU)", "bound": "pcie",
-                       "achieved": moved, "peak": h2d_gbs, "unit": "GB/s", "frac": moved / h2d_gbs,
+        moved = e2e_value * (h2d + d2h) / B / 1e9                          # GB/s the end-to-end run moved, all GPUs
+        stages.append({"stage": "staging (H2D of the segments + D2H of the results, whole job)", "bound": "pcie",
+                       "achieved": moved, "peak": h2d_box, "unit": "GB/s", "frac": moved / h2d_box,
                        "alg_per_segment": (h2d + d2h) / B, "ms": 1e3 * (h2d / (h2d_gbs * 1e9) + d2h / (d2h_gbs * 1e9)),
-                       "share": None, "peak_source": "pinned cudaMemcpyAsync H2D measured in this run (%.1f GB/s; D2H %.1f GB/s)"
-                                                     % (h2d_gbs, d2h_gbs)})
+                       "share": None, "peak_source": "pinned cudaMemcpyAsync H2D measured in this run with all %d ranks copying at once: "
+                                                     "%.1f GB/s aggregate (rank 0: %.1f GB/s, D2H %.1f GB/s)" % (world, h2d_box, h2d_gbs, d2h_gbs)})
         if dom:
             traffic, traffic_src = _ncu_traffic()
             roof = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],

@@ -165,10 +165,10 @@ class _PinnedBlock:
             raise MemoryError(f"bn_host_alloc({nbytes}) failed")
         self.nbytes = nbytes
 
-    def __del__(self):
+    def __del__(self, _free=_lib.bn_host_free):          # bound now: module globals may be gone at interpreter shutdown
         p, self.ptr = getattr(self, "ptr", None), None
         if p:
-            _lib.bn_host_free(p)
+            _free(p)
 
 
 def pinned_array(shape, dtype=np.float32) -> np.ndarray:
@@ -196,10 +196,10 @@ class BatchInferenceContext:
         self._h = handle
         self._max = max_batch_size
 
-    def __del__(self):
+    def __del__(self, _destroy=_lib.bn_ctx_destroy):     # bound now: module globals may be gone at interpreter shutdown
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _lib.bn_ctx_destroy(h)
+            _destroy(h)
 
     def max_batch_size(self) -> int:
         return int(_lib.bn_ctx_max_batch_size(self._h))
@@ -288,10 +288,10 @@ class Classifier:
         self._min_confidence = min_confidence
         self._info = info
 
-    def __del__(self):
+    def __del__(self, _destroy=_lib.bn_engine_destroy):  # bound now: module globals may be gone at interpreter shutdown
         h, self._h = getattr(self, "_h", None), None
         if h:
-            _lib.bn_engine_destroy(h)
+            _destroy(h)
 
     @staticmethod
     def builder() -> ClassifierBuilder:

@@ -25,6 +25,13 @@ def test_binding_covers_header():
     assert sorted(_ffi.SIGNATURES) == _declared()
 
 
+def test_rust_binding_lists_every_symbol():
+    """bindings/rust/birdnet_b200_sys.rs (source-only: no Rust toolchain in the image) declares exactly the header's symbols."""
+    src = open(os.path.join(ROOT, "bindings", "rust", "birdnet_b200_sys.rs")).read()
+    src = re.sub(r"//.*", "", src)
+    assert sorted(set(re.findall(r"\bpub fn (bn_[a-z0-9_]+)\s*\(", src))) == _declared()
+
+
 def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.Pred) == 8
     assert C.sizeof(_ffi.DeviceCfg) == 16
