@@ -22,6 +22,7 @@
 // FFMA2 = fma.rn.f32x2, half2 plane stores) and an XB x YB block of output pixels, so every staged
 // input value feeds several FMAs.  Sums over pixels are reduced in a fixed order -> deterministic.
 #include "kernels.h"
+#include "fast_act.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -30,7 +31,7 @@ namespace bn {
 
 namespace {
 
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_fast(float v) { return silu_approx(v); }
 
 __device__ __forceinline__ void store_pair(__half* hi, size_t plane, size_t o, float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);

@@ -2,6 +2,7 @@
 // (front-end, CNN, epilogue).  Tensor-core (tcgen05) replacements live in tc_*.cu and are
 // validated against these.
 #include "kernels.h"
+#include "fast_act.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -933,7 +934,7 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 __device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
     return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
-__device__ __forceinline__ float silu_fast_k(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_fast_k(float v) { return silu_approx(v); }
 
 template <int CIN, int STRIP>
 __global__ void __launch_bounds__(256, 2) k_stem_planes(ConvPlanesParams p) {

@@ -28,6 +28,7 @@
 //   FC weights and the projection weights are amortised over them (3x16 images: two segments per pass).
 #include "mbconv.h"
 #include "tc_common.cuh"
+#include "fast_act.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -48,7 +49,7 @@ constexpr uint32_t BOX_BYTES = 64 * 128;      // one TMA box: 64 rows x 64 fp16 
 #define MB_SERIAL_TMEM 0                      // 1: issue group g+1 only after the workers' TMEM reads of group g (measured: no gain)
 #endif
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return silu_approx(v); }
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
     unsigned long long d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -79,7 +80,7 @@ __host__ __device__ inline MbLayout mb_layout(int h, int w, int k, int cin, int 
     L.wp_stage = 2u * (uint32_t)cout * 128u;
     L.off_xa = 0;
     L.off_we = L.xa_bytes;
-    const uint32_t a_end = L.xa_bytes + 2u * L.we_stage + BOX_BYTES;     // + one box: the last M tile may read past its 64 rows
+    const uint32_t a_end = L.xa_bytes + 3u * L.we_stage + BOX_BYTES;     // three weight stages; + one box: the last M tile may read past its 64 rows
     // phase A: [X tiles | 2 expand weight stages | patch]; phase B reuses ALL of it (the patch is re-zeroed per pass):
     // [n_da D stages | 2 projection weight stages], then the FP32 staging tile of the epilogue over the same bytes
     L.off_patch = (a_end + 1023u) & ~1023u;
@@ -117,7 +118,7 @@ template <int K, int G, int XB, int YB, bool GATEA>
 __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ MbconvParams p) {
     extern __shared__ __align__(1024) uint8_t mb_smem_raw[];
     __shared__ __align__(8) uint64_t bar_x;          // block input landed
-    __shared__ __align__(8) uint64_t bar_w[2];       // expand weights of a group landed (stage = group & 1)
+    __shared__ __align__(8) uint64_t bar_w[3];       // expand weights of a group landed (stage = group % 3)
     __shared__ __align__(8) uint64_t bar_e[2];       // expand MMAs of a group complete (TMEM buffer = group & 1)
     __shared__ __align__(8) uint64_t bar_d[3];       // projection: D chunk landed (stage = chunk % n_da)
     __shared__ __align__(8) uint64_t bar_q[2];       // projection: weights of a chunk landed (stage = chunk & 1)
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ 
             mbar_init(&bar_tf[i], MB_WARPS); mbar_init(&bar_wr[i], MB_WARPS);
         }
         for (int i = 0; i < 3; ++i) { mbar_init(&bar_d[i], 1); mbar_init(&bar_g[i], MB_WARPS); }
+        mbar_init(&bar_w[2], 1);
         mbar_init(&bar_dr, MB_WARPS);
         mbar_init(&bar_sd, MB_WARPS);
         fence_barrier_init();
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ 
                 const int kc = ks >> 2, j = ks & 3;
                 const uint32_t a_hi = smem_u32(sm + L.off_xa) + ((uint32_t)(kc * 2 + 0) * (uint32_t)L.n_box + 2u * (uint32_t)m) * BOX_BYTES;
                 const uint32_t a_lo = smem_u32(sm + L.off_xa) + ((uint32_t)(kc * 2 + 1) * (uint32_t)L.n_box + 2u * (uint32_t)m) * BOX_BYTES;
-                const uint32_t wb = smem_u32(sm + L.off_we) + b * L.we_stage + (uint32_t)kc * 2u * (uint32_t)G * 128u;
+                const uint32_t wb = smem_u32(sm + L.off_we) + (gcount % 3u) * L.we_stage + (uint32_t)kc * 2u * (uint32_t)G * 128u;
                 const uint64_t db = umma_desc_sw128(wb) + (uint64_t)(kDescKStep * j);
                 umma_f16(acc, umma_desc_sw128(a_hi) + (uint64_t)(kDescKStep * j), db, idesc2, ks != 0 ? 1u : 0u);
                 umma_f16(acc + (uint32_t)G, umma_desc_sw128(a_lo) + (uint64_t)(kDescKStep * j), db, idesc1, 1u);
@@ -336,6 +338,11 @@ __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ 
     if (is_ctl) {
         // =========================== control warp: TMA, bulk copies, every tcgen05.mma ===========================
         if (elect_one()) {
+            // development aid: control-lane cycles of CTA 0 -> prof[12] wait TMEM free, [13] wait weights, [14] issue expand, [15] phase B
+            const bool cprof = p.prof != nullptr && blockIdx.x == 0;
+            unsigned long long cc[4] = {0, 0, 0, 0};
+            long long ct = cprof ? clock64() : 0;
+            auto ctick = [&](int i) { if (cprof) { const long long t = clock64(); cc[i] += (unsigned long long)(t - ct); ct = t; } };
             for (int pass = blockIdx.x; pass * P < p.batch; pass += gridDim.x, ++pass_it) {
                 const int seg0 = pass * P;
                 // previous pass: its epilogue has read TMEM and the staging tile (bar_sd), all its MMAs have retired
@@ -347,22 +354,26 @@ __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ 
                         for (int bx = 0; bx < L.n_box; ++bx)
                             tma_load_5d(sm + L.off_xa + ((uint32_t)(kc * 2 + pl) * (uint32_t)L.n_box + (uint32_t)bx) * BOX_BYTES, &p.xmap,
                                         kc * 64, seg0 * npix1 + bx * 64, 0, 0, pl, &bar_x);
-                load_we(0, gi & 1u);
-                if (n_grp > 1) load_we(1, (gi + 1u) & 1u);
+                for (int i = 0; i < 3 && i < n_grp; ++i) load_we(i, (gi + (uint32_t)i) % 3u);
                 mbar_wait(&bar_x, pass_it & 1u);
                 for (int g = 0; g < n_grp; ++g, ++gi) {
                     const uint32_t b = gi & 1u;
                     // TMEM buffer b must have been read out by the workers (group gi - 2) before it is overwritten
                     // (debug bit 64: wait for group gi - 1 instead, i.e. no MMA in flight while the workers read TMEM)
+                    ctick(3);
                     if (p.debug & 64) { if (gi >= 1u) mbar_wait(&bar_tf[b ^ 1u], ((gi - 1u) >> 1) & 1u); }
                     else if (gi >= 2u) mbar_wait(&bar_tf[b], ((gi - 2u) >> 1) & 1u);
-                    mbar_wait(&bar_w[b], (gi >> 1) & 1u);
+                    ctick(0);
+                    mbar_wait(&bar_w[gi % 3u], (gi / 3u) & 1u);
+                    ctick(1);
                     tc_fence_after();
                     issue_expand(gi);
-                    // the weight stage of group gi - 1 is free once its MMAs have retired: fetch group g + 1 into it
-                    if (g >= 1 && g + 1 < n_grp) {
+                    ctick(2);
+                    // the weight stage of group gi - 1 is free once its MMAs have retired: fetch group g + 2 into it, a whole
+                    // group period before it is needed
+                    if (g >= 1 && g + 2 < n_grp) {
                         mbar_wait(&bar_e[b ^ 1u], ((gi - 1u) >> 1) & 1u);
-                        load_we(g + 1, b ^ 1u);
+                        load_we(g + 2, (gi - 1u) % 3u);
                     }
                 }
                 // every expand MMA retired -> the operand region may take the projection's stages
@@ -390,6 +401,7 @@ __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ 
                     }
                 }
             }
+            if (cprof) for (int i = 0; i < 4; ++i) p.prof[12 + i] = cc[i];
         }
         __syncwarp();
     } else {
@@ -410,6 +422,7 @@ __global__ void __launch_bounds__(MB_BLOCK, 1) k_mbconv(const __grid_constant__ 
             const uint32_t b = gi & 1u;
             if (g + 1 < n_grp) load_wd(g + 1, b ^ 1u);               // next group's depthwise weights + biases
             const float* wgrp = s_wd + (size_t)b * WROWS * G;
+            tick(0);
             mbar_wait(&bar_e[b], (gi >> 1) & 1u);
             tc_fence_after();
             tick(1);

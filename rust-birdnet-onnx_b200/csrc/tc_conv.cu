@@ -16,6 +16,7 @@
 // smem ring: STAGES x { A_hi 16 KB | A_lo 16 KB | W_hi NT*128 B | W_lo NT*128 B }.
 #include "tc_common.cuh"
 #include "tc_conv.h"
+#include "fast_act.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,9 @@
 namespace bn {
 using namespace tc;
 
+#ifndef BN_EPI_FMA_RCP
+#define BN_EPI_FMA_RCP 0          // 1: SiLU reciprocal by Newton steps on the FMA pipe (one MUFU op instead of two); measured 1-4 % SLOWER: these phases are issue-bound, not MUFU-bound
+#endif
 constexpr int TM = 128;           // UMMA M (one TMEM lane per output row)
 constexpr int KC = 64;            // K elements per smem stage = one 128-byte swizzle row of fp16
 constexpr int MAX_STAGES = 6;
@@ -39,8 +43,8 @@ constexpr int NTHREADS_PW8 = (9 + MAX_EPI_WARPS) * 32;      // 8 producer warps 
 static int g_epi_warps_one = 16;     // BN_EPI_WARPS=8|16 (development knob)
 
 __device__ __forceinline__ float act_fn(float v, int act) {
-    if (act == KACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
-    if (act == KACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+    if (act == KACT_SILU) return silu_approx(v);
+    if (act == KACT_SIGMOID) return sigmoid_approx(v);
     return v;
 }
 
@@ -538,10 +542,10 @@ k_tc_conv(const __grid_constant__ TcConvParams p) {
                         }
                         if (p.act == KACT_SILU) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                            for (int j = 0; j < 16; ++j) v[j] = BN_EPI_FMA_RCP ? silu_fma_rcp(v[j]) : silu_approx(v[j]);
                         } else if (p.act == KACT_SIGMOID) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+                            for (int j = 0; j < 16; ++j) v[j] = sigmoid_approx(v[j]);
                         }
                         if (tma_out && gw == 32 && p.res_hi != nullptr && row_ok) {
                             // residual: this lane's row, 16 channels = one 32-byte sector per plane

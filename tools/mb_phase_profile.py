@@ -34,4 +34,4 @@ for slot in range(128):
     n = r[10]
     name = mb[k] if k < len(mb) else "?"
     k += 1
-    print(f"{name:14s} " + " ".join(f"{r[i]/n/1e3:9.2f}" for i in (0, 1, 2, 3, 8, 9, 4, 5, 6, 7)) + f" || {r[11]/n/1e3:9.2f} {int(n):4d}  {ms.get(name, 0):.4f}")
+    print(f"{name:14s} " + " ".join(f"{r[i]/n/1e3:9.2f}" for i in (0, 1, 2, 3, 8, 9, 4, 5, 6, 7)) + f" | ctl: tf {r[12]/n/1e3:.1f} w {r[13]/n/1e3:.1f} issue {r[14]/n/1e3:.1f} rest {r[15]/n/1e3:.1f}" + f" || {r[11]/n/1e3:9.2f} {int(n):4d}  {ms.get(name, 0):.4f}")
