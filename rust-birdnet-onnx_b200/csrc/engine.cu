@@ -5,6 +5,7 @@
 // monitor), 676-727 (predict_batch), 826-867 (predict_batch_with_context);
 // src/batch_context.rs:102-133, 188-338.
 #include "engine.h"
+#include "frontend_v24.h"
 #include "hostcopy.h"
 
 #include <algorithm>
@@ -315,6 +316,43 @@ int engine_create(const char* path, const bn_device_cfg* cfg, bn_engine** out) {
                 e->fe_tc.push_back(ft);
             }
         }
+        // one kernel for normaliser + both spectrogram GEMMs (BN_DISABLE_FE_FUSED=1 keeps the frame-matrix path for A/B runs)
+        const char* nofe = getenv("BN_DISABLE_FE_FUSED");
+        const size_t nb = p.fe.branches.size();
+        if (e->tc_mode && p.fe.normalize && !(nofe && nofe[0] == '1') && nb >= 1 && nb <= 2) {
+            SpecBranchHost hb[2];
+            bool ok = true;
+            for (size_t bi = 0; bi < nb && ok; ++bi) {
+                const SpecBranch& br = p.fe.branches[bi];
+                ok = spec_v24_plan(br.n_fft, br.hop, br.n_mels, hb[bi]) && br.n_frames == p.fe.branches[0].n_frames &&
+                     br.n_mels == p.fe.branches[0].n_mels;
+            }
+            auto& fv = e->fe_v24;
+            int order[2] = {0, 1};
+            if (ok && nb == 2 && hb[1].table.size() > hb[0].table.size()) { order[0] = 1; order[1] = 0; std::swap(hb[0], hb[1]); }
+            ok = ok && spec_v24_layout(hb, (int)nb, fv.row_pitch, fv.patch_plane, fv.n_stages, fv.smem_bytes);
+            if (ok) {
+                BN_CUDA(spec_v24_init_device());
+                for (size_t sl = 0; sl < nb; ++sl) {
+                    const int bi = order[sl];
+                    const SpecBranch& br = p.fe.branches[bi];
+                    std::vector<float> basis;
+                    int ldb = 0;
+                    build_real_mel_basis(br, basis, ldb);
+                    std::vector<uint16_t> pack;
+                    spec_v24_pack(hb[sl], basis.data(), ldb, br.n_fft, br.n_mels, pack);
+                    BN_CUDA(cudaMalloc(&fv.wpack[sl], pack.size() * sizeof(uint16_t)));
+                    BN_CUDA(cudaMemcpy(fv.wpack[sl], pack.data(), pack.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    fv.slot_branch[sl] = bi;
+                    fv.hop[sl] = hb[sl].hop; fv.kcells[sl] = hb[sl].kcells; fv.rows[sl] = hb[sl].rows;
+                    fv.blocks[sl] = hb[sl].blocks; fv.split[sl] = hb[sl].split; fv.pad[sl] = hb[sl].pad;
+                    fv.n_ksteps[sl] = (int)hb[sl].table.size();
+                }
+                fv.n_br = (int)nb;
+                fv.n_pad = hb[0].n_pad;
+                fv.on = true;
+            }
+        }
     } else {
         if (!tc_enabled) return set_error(BN_ERR_MODEL_LOAD, "the log-mel front-end needs the tensor-core (planes) path; unset BN_DISABLE_TC");
         const SpecBranch& br = p.fe.branches[0];
@@ -373,6 +411,7 @@ bn_engine::~bn_engine() {
     }
     for (auto* b : d_basis) cudaFree(b);
     for (auto& f : fe_tc) if (f.wpack) cudaFree(f.wpack);
+    for (int i = 0; i < 2; ++i) if (fe_v24.wpack[i]) cudaFree(fe_v24.wpack[i]);
     if (fe_lm.window) cudaFree(fe_lm.window);
     if (fe_lm.twiddle) cudaFree(fe_lm.twiddle);
     if (fe_lm.mel_lo) cudaFree(fe_lm.mel_lo);
@@ -451,6 +490,7 @@ int ctx_create(bn_engine* e, uint64_t max_batch, bn_ctx** out) {
     if (p.fe.normalize) BN_CUDA(cudaMalloc(&c->d_norm, mb * S * sizeof(float)));
     BN_CUDA(cudaMalloc(&c->d_minmax, mb * 2 * sizeof(uint32_t)));
     { const char* kn = getenv("BN_KEEP_NORMALIZED"); c->keep_normalized = !e->tc_mode || (kn && kn[0] == '1'); }
+    if (!e->fe_v24.on)
     for (auto& ft : e->fe_tc) {
         __half* x = nullptr;
         BN_CUDA(cudaMalloc(&x, 2 * mb * (size_t)ft.rows * ft.row_stride * sizeof(__half)));
@@ -821,7 +861,35 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
     const float* fe_in = d_audio;
     if (p.fe.kind != FE_LOGMEL) prof_mark(c, "normalize");
     const bool fe_on_tc = e->tc_mode && !e->fe_tc.empty() && p.fe.normalize;
-    if (fe_on_tc) {
+    const bool fe_fused = fe_on_tc && e->fe_v24.on;
+    if (fe_fused) {
+        // min / max per segment (and, for tests only, the FP32 normalised copy); the spectrogram kernel normalises on the fly
+        BN_CUDA(launch_minmax_normalize_fe(d_audio, c->keep_normalized ? c->d_norm : nullptr, c->d_minmax, nullptr, 0,
+                                           B, p.sample_count, p.fe.eps, p.fe.half, p.fe.two, s));
+        launches += c->keep_normalized ? 3 : 2;
+        prof_mark(c, "spectrogram");
+        const auto& fv = e->fe_v24;
+        PlanesPtr o = planes_of(c, p.fe.out_tensor);
+        SpecV24Params sp{};
+        sp.audio = d_audio; sp.minmax = c->d_minmax; sp.n_br = fv.n_br;
+        for (int sl = 0; sl < fv.n_br; ++sl) {
+            const SpecBranch& br = p.fe.branches[fv.slot_branch[sl]];
+            sp.br[sl] = SpecBranchDev{fv.wpack[sl], fv.hop[sl], fv.kcells[sl], fv.rows[sl], fv.blocks[sl], fv.split[sl], fv.pad[sl],
+                                      fv.n_ksteps[sl], fv.slot_branch[sl], br.exponent};
+        }
+        const SpecBranch& b0 = p.fe.branches[0];
+        sp.out_hi = o.hi; sp.out_plane = o.plane;
+        sp.batch = B; sp.S = p.sample_count; sp.n_frames = b0.n_frames; sp.n_mels = b0.n_mels; sp.n_pad = fv.n_pad;
+        sp.n_ch = (int)p.fe.branches.size(); sp.tiles_per_seg = (b0.n_frames + 127) / 128;
+        sp.row_pitch = fv.row_pitch; sp.n_stages = fv.n_stages; sp.patch_plane = fv.patch_plane;
+        { static const int ns = [] { const char* ev = getenv("BN_FE_STAGES"); return ev ? atoi(ev) : 0; }(); if (ns >= 2 && ns < sp.n_stages) sp.n_stages = ns; }
+        sp.eps = p.fe.eps; sp.half = p.fe.half; sp.two = p.fe.two;
+        { static const int dbg = [] { const char* ev = getenv("BN_FE_DEBUG"); return ev ? atoi(ev) : 0; }(); sp.debug = dbg; }
+        sp.prof = c->profiling && getenv("BN_FE_PROFILE") ? tc_conv_prof_slot(127) : nullptr;
+        BN_CUDA(launch_spec_v24(sp, fv.smem_bytes, e->num_sms, s));
+        ++launches;
+        fe_in = c->d_norm;
+    } else if (fe_on_tc) {
         const size_t mb = std::max<uint64_t>(c->max_batch, 1);
         FePlaneOut outs[2];
         for (size_t bi = 0; bi < e->fe_tc.size(); ++bi) {
@@ -854,7 +922,7 @@ static int enqueue_forward(bn_ctx* c, const float* d_audio, int B, const PostCfg
         lp.out_f32 = nullptr;
         BN_CUDA(launch_logmel(lp, s));
         ++launches;
-    } else
+    } else if (!fe_fused)
     for (size_t bi = 0; bi < p.fe.branches.size(); ++bi) {
         const SpecBranch& br = p.fe.branches[bi];
         prof_mark(c, bi == 0 ? "spectrogram0" : "spectrogram1");

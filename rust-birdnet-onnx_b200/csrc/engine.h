@@ -81,6 +81,14 @@ struct bn_engine {
     // tensor-core front-end: per branch the block-Toeplitz frame matrix geometry + packed basis
     struct FeTc { void* wpack = nullptr; int hop = 0, row_stride = 0, rows = 0, K = 0, nt = 0, n_tiles = 0, k_chunks = 0, stages = 2, tmem_cols = 32; };
     std::vector<FeTc> fe_tc;
+    // fused v2.4 front-end (frontend_v24.cu): replaces the frame-matrix planes + per-branch GEMMs when the shapes fit
+    struct FeV24 {
+        bool on = false;
+        void* wpack[2] = {nullptr, nullptr};
+        int slot_branch[2] = {0, 0};      // kernel slot -> front-end branch index (slot 0 = longer K loop)
+        int hop[2] = {0, 0}, kcells[2] = {0, 0}, rows[2] = {0, 0}, n_ksteps[2] = {0, 0}, blocks[2] = {0, 0}, split[2] = {0, 0}, pad[2] = {0, 0};
+        int n_br = 0, n_pad = 0, row_pitch = 0, n_stages = 0; uint32_t patch_plane = 0, smem_bytes = 0;
+    } fe_v24;
     // log-mel front-end (32 kHz graphs): window, float64-built twiddles, banded mel filters
     struct FeLogmel {
         float* window = nullptr; float* twiddle = nullptr; int* mel_lo = nullptr; int* mel_cnt = nullptr; int* mel_off = nullptr;

@@ -1,0 +1,515 @@
+// BirdNET v2.4-style audio front-end, ONE kernel for both mel-spectrogram branches (the reference has this
+// arithmetic inside the model file it feeds to ONNX Runtime, src/classifier.rs:851-853 — there is no reference source for it).
+//
+//   spec[b][mel][t][branch] = pow( ( sum_n  xn[b][t*hop + n] * basis[n][mel] )^2 , exponent )
+//   xn = ((x - min) / (max - min + eps) - half) * two            (per segment; min / max come from k_minmax_partial)
+//
+// What the kernel moves: the raw FP32 audio once per branch (L2-resident after the min/max pass) and the spectrogram out.
+// No normalised copy and no frame matrix ever exists in HBM:
+//
+//   producer warps   read the raw samples of one 128-frame tile, normalise them (same formula as the stand-alone
+//                    normaliser, division by reciprocal + residual correction), split to fp16 hi / lo and store them as a SAMPLE PATCH in shared memory:
+//                    patch row p = the `hop` samples starting at (t0 + p) * hop, kept as 16-byte cells [kcell][row].
+//                    Frame t0 + i is then rows i, i+1, ... read left to right (block-Toeplitz): the K range of block j is
+//                    the same cells shifted j rows down, which for a no-swizzle K-major UMMA operand is a start-address
+//                    shift of j * 16 bytes.  135 rows x 35 cells x 2 planes = 152 KB instead of 128 x 2240 x 2 x 2 = 1.1 MB.
+//   loader warp      streams the packed basis [k-step][W_hi | W_lo] through a ring of 1-D bulk copies (12 KB per stage).
+//   control warp     one elected lane issues, per 16-sample K step, hi * [W_hi | W_lo] (N = 2 * mels: main | correction)
+//                    and lo * W_hi (N = mels, into the correction half) into one of two TMEM accumulator sets.
+//   epilogue warps   TMEM -> square -> power-compress -> hi / lo planes of the [mel][frame][branch] image the stem reads,
+//                    overlapped with the MMAs of the next tile (second accumulator set).
+//
+// The K loop runs cell-column pair by cell-column pair (all blocks j of a pair before the next pair), so a column pair of
+// the patch is dead as soon as its MMAs have completed: the producers refill it for the NEXT tile while the MMAs of this
+// tile are still running on the later columns.  The patch is its own double buffer.
+#include "frontend_v24.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#ifndef SV_SPIN_WAIT
+#define SV_SPIN_WAIT 0
+#endif
+#if SV_SPIN_WAIT
+#define BN_MBAR_TRY_WAIT 0
+#endif
+#include "tc_common.cuh"
+
+namespace bn {
+using namespace tc;
+
+namespace {
+
+constexpr int SV_EPI_WARPS = 8;                     // two per TMEM lane quarter (alternate 16-column chunks)
+constexpr int SV_PROD_WARPS = 10;
+constexpr int SV_WARPS = 2 + SV_EPI_WARPS + SV_PROD_WARPS;      // control, loader, epilogue, producers
+constexpr int SV_THREADS = SV_WARPS * 32;
+constexpr int SV_MAX_GROUPS = 24;                   // cell-column pairs of the patch
+constexpr int SV_MAX_STAGES = 12;
+constexpr uint32_t SV_FIRST = 1u << 24, SV_LAST = 1u << 25;   // K-step table flags: first / last step of a column pair
+constexpr uint32_t SV_SMEM_MAX = 224 * 1024;        // + the static barriers stays under the 227 KB block limit
+
+__device__ __forceinline__ float sv_key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ void sv_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// the single-lane roles address their barriers by 32-bit shared address (formed once, outside the loops)
+__device__ __forceinline__ void sv_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (++spins > (1u << 28)) __trap();
+    } while (!ok);
+}
+template <bool PROF>
+__device__ __forceinline__ void sv_wait1(uint32_t bar, uint32_t parity, unsigned long long& acc) {
+    if (!PROF) { sv_wait_u32(bar, parity); return; }
+    const long long t0 = clock64();
+    sv_wait_u32(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
+// keeps an address the compiler would otherwise re-derive (S2UR SR_CgaCtaId + ULEA per use) in a register
+__device__ __forceinline__ uint32_t sv_opaque(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void sv_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sv_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sv_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <bool PROF>
+__device__ __forceinline__ void sv_wait(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
+    if (!PROF) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+}
+
+extern __shared__ __align__(16) uint8_t sv_smem_raw[];
+
+// tile n of this CTA -> (branch slot, segment, first frame).  Slot 0 (the longer K loop) is dealt round-robin from CTA 0
+// up, slot 1 from the last CTA down, so a CTA that got one more long tile gets one fewer short tile.
+struct SvTile { int slot, seg, t0; };
+__device__ __forceinline__ bool sv_tile(const SpecV24Params& p, int n, SvTile& t) {
+    const int grid = (int)gridDim.x, bx = (int)blockIdx.x;
+    const int per = p.batch * p.tiles_per_seg;
+    const int mine0 = bx < per ? (per - 1 - bx) / grid + 1 : 0;
+    int idx;
+    if (n < mine0) {
+        t.slot = 0;
+        idx = bx + n * grid;
+    } else {
+        if (p.n_br < 2) return false;
+        t.slot = 1;
+        idx = (grid - 1 - bx) + (n - mine0) * grid;
+        if (idx >= per) return false;
+    }
+    t.seg = idx / p.tiles_per_seg;
+    t.t0 = (idx - t.seg * p.tiles_per_seg) * 128;
+    return true;
+}
+
+// K steps of cell-column pair m: all blocks that still have weighted cells there, + the zero-weight step that makes the
+// total even... (the packed basis has the same order: spec_v24_plan)
+__device__ __forceinline__ int sv_group_steps(const SpecBranchDev& br, int m, int groups) {
+    return (m < br.split ? br.blocks : br.blocks - 1) + (m == groups - 1 ? br.pad : 0);
+}
+
+// index of the first K step of pair m in the packed basis
+__device__ __forceinline__ int sv_group_first(const SpecBranchDev& br, int m) { return m * (br.blocks - 1) + min(m, br.split); }
+// Order of the column pairs: the same for every CTA (a per-CTA rotation was tried to spread the basis reads over L2 — no
+// effect on time, and it would make a segment's bits depend on its position in the batch).
+__device__ __forceinline__ int sv_rot(const SpecV24Params&, int) { return 0; }
+
+template <bool PROF>
+__global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params p) {
+    __shared__ __align__(8) uint64_t g_full[SV_MAX_GROUPS];     // patch column pair written (producer warp -> control)
+    __shared__ __align__(8) uint64_t g_empty[SV_MAX_GROUPS];    // its MMAs completed (tcgen05.commit -> producers)
+    __shared__ __align__(8) uint64_t w_full[SV_MAX_STAGES];     // basis ring slot (two K steps) landed (bulk copy -> control)
+    __shared__ __align__(8) uint64_t w_empty[SV_MAX_STAGES];    // its MMAs completed (tcgen05.commit -> loader)
+    __shared__ __align__(8) uint64_t acc_full[2];               // all MMAs of a tile completed (-> epilogue)
+    __shared__ __align__(8) uint64_t acc_empty[2];              // accumulator set read out (epilogue warps -> control)
+    __shared__ uint32_t tmem_holder;
+    __shared__ __align__(8) uint32_t s_tab[2][SV_MAX_KSTEPS];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* sm = sv_smem_raw + ((128u - (smem_u32(sv_smem_raw) & 127u)) & 127u);
+    const uint32_t plane = p.patch_plane;                       // bytes of one patch plane (hi; lo follows)
+    uint8_t* patch = sm;
+    uint8_t* wring = sm + 2u * plane;
+    const uint32_t N = (uint32_t)p.n_pad;                       // mel columns, multiple of 16
+    const uint32_t kstep_bytes = 64u * N;                       // [2 cells][2N rows][16 B]
+    const uint32_t NS = (uint32_t)p.n_stages;
+
+    if (tid == 0) {
+        for (int i = 0; i < SV_MAX_GROUPS; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
+        for (int i = 0; i < SV_MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SV_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    // K-step table of this CTA (its own rotation of the column pairs): patch offset in 16-byte cells | pair << 16 | flags
+    if (tid < p.n_br) {
+        const SpecBranchDev& br = p.br[tid];
+        const int groups = (br.kcells + 1) >> 1;
+        const int rot = sv_rot(p, groups);
+        int ks = 0;
+        for (int mi = 0; mi < groups; ++mi) {
+            const int m = mi + rot < groups ? mi + rot : mi + rot - groups;
+            const int jn = sv_group_steps(br, m, groups);
+            for (int j = 0; j < jn; ++j, ++ks)
+                s_tab[tid][ks] = ((uint32_t)m * 2u * (uint32_t)p.row_pitch + (uint32_t)j) | ((uint32_t)m << 16) |
+                                 (j == 0 ? SV_FIRST : 0u) | (j == jn - 1 ? SV_LAST : 0u);
+        }
+    }
+    // the whole patch starts as zeros: rows and cells no producer writes are still read (with zero weights, or for frames
+    // past the end that are never stored), so they must hold finite numbers
+    for (uint32_t i = tid; i < 2u * plane / 16u; i += SV_THREADS) reinterpret_cast<uint4*>(patch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    if (warp == 0) tmem_alloc(&tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+    // development aid (PROF): cycles of CTA 0.  control [0] wait accumulator free [1] wait patch columns [2] wait basis step
+    // [3] total [4] tiles | producer warp 0: [5] wait columns free [6] total | epilogue warp 0: [7] wait MMAs [8] total |
+    // loader: [9] wait ring slot [10] total
+    const bool prof = PROF && p.prof != nullptr && blockIdx.x == 0;
+    unsigned long long pc0 = 0, pc1 = 0, pc2 = 0;
+    const long long t_begin = PROF ? clock64() : 0;
+
+    if (warp == 0) {
+        // ================================ control: every tcgen05.mma ================================
+        // One lane runs this loop and nothing else; it has to stay under the ~144 cycles the two MMAs of a K step take, so
+        // everything is plain 32-bit shared addresses and counters: one wait + one commit per ring slot (two K steps), one
+        // wait + one commit per column pair.
+        if (elect_one()) {
+            const uint32_t idesc2 = umma_idesc_f16(128, (int)(2u * N)), idesc1 = umma_idesc_f16(128, (int)N);
+            // descriptors without the start-address field; the field is (shared address >> 4), all addresses < 256 KB
+            const uint64_t da_hi0 = umma_desc_nosw(smem_u32(patch), (uint32_t)p.row_pitch * 16u, 128u);
+            const uint64_t da_lo0 = da_hi0 + (uint64_t)(plane >> 4);
+            const uint64_t db0 = umma_desc_nosw(smem_u32(wring), 2u * N * 16u, 128u);
+            const uint32_t step16 = kstep_bytes >> 4;
+            const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0]));
+            const uint32_t gf0 = sv_opaque(smem_u32(&g_full[0])), ge0 = sv_opaque(smem_u32(&g_empty[0]));
+            const uint32_t af0 = sv_opaque(smem_u32(&acc_full[0])), ae0 = sv_opaque(smem_u32(&acc_empty[0]));
+            uint32_t st = 0, wph = 0;                           // basis ring: slot, parity
+            SvTile t;
+            for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
+                const uint32_t as = it & 1u;
+                sv_wait1<PROF>(ae0 + 8u * as, ((it >> 1) & 1u) ^ 1u, pc0);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + as * 2u * N;
+                const uint2* tab = reinterpret_cast<const uint2*>(s_tab[t.slot]);
+                const int nslots = p.br[t.slot].n_ksteps >> 1;
+                const uint32_t gpar = it & 1u;
+                uint32_t accum = 0;
+                for (int s2 = 0; s2 < nslots; ++s2) {
+                    const uint2 e = tab[s2];                    // the two K steps of this ring slot
+                    sv_wait1<PROF>(wf0 + 8u * st, wph, pc2);
+                    const uint64_t db = db0 + (uint64_t)(2u * st * step16);
+                    if (e.x & SV_FIRST) sv_wait1<PROF>(gf0 + ((e.x >> 13) & 0x7F8u), gpar, pc1);
+                    tc_fence_after();
+                    umma_f16(acc, da_hi0 + (uint64_t)(e.x & 0xFFFFu), db, idesc2, accum);
+                    umma_f16(acc + N, da_lo0 + (uint64_t)(e.x & 0xFFFFu), db, idesc1, 1u);
+                    if (e.x & SV_LAST) sv_commit(ge0 + ((e.x >> 13) & 0x7F8u));
+                    if (e.y & SV_FIRST) { sv_wait1<PROF>(gf0 + ((e.y >> 13) & 0x7F8u), gpar, pc1); tc_fence_after(); }
+                    umma_f16(acc, da_hi0 + (uint64_t)(e.y & 0xFFFFu), db + step16, idesc2, 1u);
+                    umma_f16(acc + N, da_lo0 + (uint64_t)(e.y & 0xFFFFu), db + step16, idesc1, 1u);
+                    if (e.y & SV_LAST) sv_commit(ge0 + ((e.y >> 13) & 0x7F8u));
+                    sv_commit(we0 + 8u * st);
+                    accum = 1u;
+                    if (++st == NS) { st = 0; wph ^= 1u; }
+                }
+                sv_commit(af0 + 8u * as);
+                if (prof) p.prof[4] = it + 1;
+            }
+            if (prof) { p.prof[0] = pc0; p.prof[1] = pc1; p.prof[2] = pc2; p.prof[3] = (unsigned long long)(clock64() - t_begin); }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================ loader: basis ring, two K steps per slot ================================
+        // (the packed basis is walked group by group in this CTA's rotated order; a slot may straddle two groups)
+        if (elect_one()) {
+            const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0])), ring0 = sv_opaque(smem_u32(wring));
+            uint32_t st = 0, wph = 1, half = 0;
+            SvTile t;
+            for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
+                const SpecBranchDev& br = p.br[t.slot];
+                const int groups = (br.kcells + 1) >> 1;
+                const int rot = sv_rot(p, groups);
+                for (int mi = 0; mi < groups; ++mi) {
+                    const int m = mi + rot < groups ? mi + rot : mi + rot - groups;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(br.wpack) + (size_t)sv_group_first(br, m) * kstep_bytes;
+                    int left = sv_group_steps(br, m, groups);
+                    while (left > 0) {
+                        // as many K steps as are contiguous in the packed basis AND in the slot: 1 or 2
+                        const int n = (half == 0 && left >= 2) ? 2 : 1;
+                        if (half == 0) {
+                            sv_wait1<PROF>(we0 + 8u * st, wph, pc0);
+                            sv_expect_tx(wf0 + 8u * st, 2u * kstep_bytes);
+                        }
+                        sv_bulk_g2s(ring0 + (2u * st + half) * kstep_bytes, src, (uint32_t)n * kstep_bytes, wf0 + 8u * st);
+                        src += (size_t)n * kstep_bytes;
+                        left -= n;
+                        half += (uint32_t)n;
+                        if (half == 2) { half = 0; if (++st == NS) { st = 0; wph ^= 1u; } }
+                    }
+                }
+            }
+            if (prof) { p.prof[9] = pc0; p.prof[10] = (unsigned long long)(clock64() - t_begin); }
+        }
+        __syncwarp();
+    } else if (warp < 2 + SV_EPI_WARPS) {
+        // ================================ epilogue ================================
+        const uint32_t q = (uint32_t)warp & 3u;                 // TMEM lane quarter this warp may read
+        const uint32_t par = (uint32_t)(warp - 2) >> 2;         // which of the alternating 16-column chunks
+        SvTile t;
+        for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
+            const SpecBranchDev& br = p.br[t.slot];
+            const uint32_t as = it & 1u;
+            sv_wait<PROF>(&acc_full[as], (it >> 1) & 1u, pc0);
+            tc_fence_after();
+            const int tt = t.t0 + (int)q * 32 + lane;
+            const bool row_ok = tt < p.n_frames;
+            const uint32_t t_lane = tmem_base + ((q * 32u) << 16) + as * 2u * N;
+            const size_t mel_stride = (size_t)p.n_frames * p.n_ch;
+            __half* out = p.out_hi + ((size_t)t.seg * p.n_mels * p.n_frames + (size_t)tt) * p.n_ch + br.ch;
+            const float ex = br.exponent;
+            for (uint32_t c0 = par * 16u; c0 < N; c0 += 16u * (SV_EPI_WARPS / 4)) {
+                uint32_t rm[16], rc[16];
+                tmem_ld16_nowait(t_lane + c0, rm);
+                tmem_ld16_nowait(t_lane + N + c0, rc);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if ((int)c0 + j < p.n_mels) {
+                            const float v = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+                            const float pw = v * v;
+                            const float r = pw > 0.f ? exp2f(ex * __log2f(pw)) : pw;
+                            __half* o = out + (size_t)(c0 + j) * mel_stride;
+                            const __half hh = __float2half_rn(r);
+                            o[0] = hh;
+                            o[p.out_plane] = __float2half_rn(r - __half2float(hh));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (prof && warp == 2 && lane == 0) { p.prof[7] = pc0; p.prof[8] = (unsigned long long)(clock64() - t_begin); }
+    } else {
+        // ================================ producers: raw audio -> normalised hi / lo sample patch ================================
+        const int pw = warp - 2 - SV_EPI_WARPS;
+        const uint32_t RP = (uint32_t)p.row_pitch;
+        SvTile t;
+        for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
+            const SpecBranchDev& br = p.br[t.slot];
+            const float* xs = p.audio + (size_t)t.seg * p.S;
+            float lo = sv_key2f(__ldg(p.minmax + 2 * t.seg));
+            const float hi_v = sv_key2f(__ldg(p.minmax + 2 * t.seg + 1));
+            if (hi_v != hi_v) lo = hi_v;                        // any NaN poisons the whole segment, like torch
+            const float den = __fadd_rn(__fsub_rn(hi_v, lo), p.eps);
+            const float rden = __frcp_rn(den);
+            const bool den_ok = den > 1e-30f && den < 1e30f;    // otherwise (NaN / Inf / denormal range) take the IEEE division
+            const int groups = (br.kcells + 1) >> 1;
+            const bool even_hop = (br.hop & 1) == 0;
+            // the samples of a tile are one contiguous range: pull the NEXT tile's range into L2 while this one is converted
+            // (the audio is larger than L2, so after the min/max pass most of it is back in HBM)
+            if (pw == 0 && lane == 0) {
+                SvTile nt;
+                if (sv_tile(p, (int)it + 1, nt)) {
+                    const SpecBranchDev& nb = p.br[nt.slot];
+                    const long long s_beg = (long long)nt.t0 * nb.hop;
+                    long long s_end = s_beg + (long long)nb.rows * nb.hop + 16;
+                    if (s_end > p.S) s_end = p.S;
+                    const float* g = p.audio + (size_t)nt.seg * p.S + s_beg;
+                    const uintptr_t a0 = reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15;
+                    const uint32_t bytes = (uint32_t)(((reinterpret_cast<uintptr_t>(g) + (size_t)(s_end - s_beg) * 4 - a0) + 15) & ~(size_t)15);
+                    if (s_end > s_beg && !(p.debug & 256))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+                }
+            }
+            const int rot = sv_rot(p, groups);
+            for (int mi = pw; mi < groups; mi += SV_PROD_WARPS) {
+                const int m = mi + rot < groups ? mi + rot : mi + rot - groups;
+                sv_wait<PROF>(&g_empty[m], (it & 1u) ^ 1u, pc0);
+                uint8_t* col = patch + (size_t)(2 * m) * RP * 16u;          // cells 2m (and 2m + 1, RP cells further)
+                const bool two = 2 * m + 1 < br.kcells;                     // odd cell count: the last pair has one weighted cell
+                if (!(p.debug & 1))
+                for (int r0 = lane; r0 < br.rows; r0 += 64) {
+                    // two rows per pass, every load issued before the first use
+                    float v[2][16];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int r = r0 + 32 * u;
+                        const int s0 = (t.t0 + r) * br.hop + m * 16;
+                        if (r < br.rows && even_hop && s0 + 16 <= p.S) {
+                            const float2* g = reinterpret_cast<const float2*>(xs + s0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { const float2 f = __ldg(g + i); v[u][2 * i] = f.x; v[u][2 * i + 1] = f.y; }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[u][i] = (r < br.rows && s0 + i < p.S) ? __ldg(xs + s0 + i) : lo;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int r = r0 + 32 * u;
+                        if (r >= br.rows) break;
+                        const int nvalid = p.S - ((t.t0 + r) * br.hop + m * 16);     // samples past the segment end stay exactly zero
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            // (x - lo) / den as reciprocal + one residual correction: the IEEE quotient in all but rare
+                            // half-ulp cases, at 3 instructions instead of the ~18 of __fdiv_rn (the producers were issue-bound);
+                            // the value is split to 22 bits right after, the FP32 normalised copy the tests read is not made here
+                            const float a = __fsub_rn(v[u][i], lo);
+                            const float q0 = __fmul_rn(a, rden);
+                            const float q = __fmaf_rn(__fmaf_rn(-q0, den, a), rden, q0);
+                            const float xn = __fmul_rn(__fsub_rn(den_ok ? q : __fdiv_rn(a, den), p.half), p.two);
+                            v[u][i] = i < nvalid ? xn : 0.f;
+                        }
+                        uint4 h, l;
+                        split8(v[u], h, l);
+                        *reinterpret_cast<uint4*>(col + (size_t)r * 16u) = h;
+                        *reinterpret_cast<uint4*>(col + plane + (size_t)r * 16u) = l;
+                        if (two) {
+                            split8(v[u] + 8, h, l);
+                        } else {
+                            h = make_uint4(0u, 0u, 0u, 0u);
+                            l = h;
+                        }
+                        *reinterpret_cast<uint4*>(col + (size_t)(RP + r) * 16u) = h;
+                        *reinterpret_cast<uint4*>(col + plane + (size_t)(RP + r) * 16u) = l;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&g_full[m]);
+            }
+        }
+        if (prof && pw == 0 && lane == 0) { p.prof[5] = pc0; p.prof[6] = (unsigned long long)(clock64() - t_begin); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+static inline uint16_t sv_f2h(float f) {
+    return __half_raw(__float2half_rn(f)).x;
+}
+static inline float sv_h2f(uint16_t u) {
+    __half_raw r;
+    r.x = u;
+    return __half2float(__half(r));
+}
+
+bool spec_v24_plan(int n_fft, int hop, int n_mels, SpecBranchHost& out) {
+    out = SpecBranchHost{};
+    if (hop <= 0 || n_fft < hop || n_mels <= 0 || n_mels > 128) return false;
+    out.hop = hop;
+    out.kcells = (hop + 7) / 8;
+    out.blocks = (n_fft + hop - 1) / hop;
+    out.rows = 128 + out.blocks - 1;
+    out.n_pad = (n_mels + 15) / 16 * 16;
+    const int last_w = n_fft - (out.blocks - 1) * hop;
+    const int last_cells = (last_w + 7) / 8;
+    const int groups = (out.kcells + 1) / 2;
+    if (groups > SV_MAX_GROUPS) return false;
+    out.split = std::min(groups, (last_cells + 1) / 2);
+    out.table.clear();
+    for (int m = 0; m < groups; ++m) {
+        const int jn = m < out.split ? out.blocks : out.blocks - 1;
+        for (int j = 0; j < jn; ++j) out.table.push_back(SpecKStep{m, j, false});
+    }
+    out.pad = (int)(out.table.size() & 1);
+    if (out.pad) {                              // an even count keeps the ring arithmetic simple: one zero-weight step at the
+        const int m = groups - 1;               // end of the last group, one more block down (rows it reads exist and are finite)
+        out.table.push_back(SpecKStep{m, (m < out.split ? out.blocks : out.blocks - 1), true});
+        out.rows_read = std::max(out.rows, 128 + out.table.back().j);
+    } else {
+        out.rows_read = out.rows;
+    }
+    return (int)out.table.size() <= SV_MAX_KSTEPS;
+}
+
+void spec_v24_pack(const SpecBranchHost& b, const float* basis, int ldb, int n_fft, int n_mels, std::vector<uint16_t>& wpack) {
+    const int N = b.n_pad;
+    wpack.assign((size_t)b.table.size() * 2 * 2 * N * 8, 0);
+    for (size_t ks = 0; ks < b.table.size(); ++ks) {
+        const SpecKStep& k = b.table[ks];
+        if (k.zero) continue;
+        uint16_t* dst = wpack.data() + ks * (size_t)(2 * 2 * N * 8);
+        for (int kc = 0; kc < 2; ++kc)
+            for (int kk = 0; kk < 8; ++kk) {
+                const int col = (2 * k.m + kc) * 8 + kk;
+                const int n = k.j * b.hop + col;
+                if (col >= b.hop || n >= n_fft) continue;
+                for (int mel = 0; mel < n_mels; ++mel) {
+                    const float w = basis[(size_t)n * ldb + mel];
+                    const uint16_t h = sv_f2h(w);
+                    dst[((size_t)kc * 2 * N + mel) * 8 + kk] = h;
+                    dst[((size_t)kc * 2 * N + N + mel) * 8 + kk] = sv_f2h(w - sv_h2f(h));
+                }
+            }
+    }
+}
+
+bool spec_v24_layout(const SpecBranchHost* br, int n_br, int& row_pitch, uint32_t& patch_plane, int& n_stages, uint32_t& smem_bytes) {
+    int rows = 0, cols = 0, n_pad = 0;
+    for (int i = 1; i < n_br; ++i)
+        if ((br[i].kcells + 1) / 2 != (br[0].kcells + 1) / 2) return false;     // the group barriers flip once per tile
+    for (int i = 0; i < n_br; ++i) {
+        rows = std::max(rows, br[i].rows_read);
+        cols = std::max(cols, (br[i].kcells + 1) / 2 * 2);
+        if (n_pad && n_pad != br[i].n_pad) return false;
+        n_pad = br[i].n_pad;
+    }
+    row_pitch = (rows + 7) / 8 * 8;
+    patch_plane = (uint32_t)cols * (uint32_t)row_pitch * 16u;
+    const uint32_t stage = 128u * (uint32_t)n_pad;           // a ring slot = two K steps
+    const uint32_t fixed = 2u * patch_plane + 128u;
+    if (fixed + 2u * stage > SV_SMEM_MAX) return false;
+    n_stages = (int)std::min<uint32_t>((SV_SMEM_MAX - fixed) / stage, SV_MAX_STAGES);
+    smem_bytes = fixed + (uint32_t)n_stages * stage;
+    return 2 * 2 * n_pad <= 512 && n_stages >= 2;
+}
+
+cudaError_t spec_v24_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_spec_v24<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_spec_v24<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX);
+}
+
+cudaError_t launch_spec_v24(const SpecV24Params& p, uint32_t smem_bytes, int num_sms, cudaStream_t stream) {
+    if (p.batch <= 0) return cudaSuccess;
+    const int per = p.batch * p.tiles_per_seg;
+    const int grid = std::min(num_sms, per);
+    if (p.prof) k_spec_v24<true><<<grid, SV_THREADS, smem_bytes, stream>>>(p);
+    else k_spec_v24<false><<<grid, SV_THREADS, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace bn

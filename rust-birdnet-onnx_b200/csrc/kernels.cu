@@ -269,7 +269,7 @@ cudaError_t launch_minmax_normalize_fe(const float* x, float* y, uint32_t* minma
     k_minmax_init<<<(batch + 255) / 256, 256, 0, stream>>>(minmax_scratch, batch);
     dim3 grid(NORM_SLICES, batch);
     k_minmax_partial<<<grid, 512, 0, stream>>>(x, minmax_scratch, sample_count);
-    k_normalize_emit<<<grid, 512, 0, stream>>>(x, y, minmax_scratch, fo, sample_count, eps, half, two);
+    if (y != nullptr || n_outs > 0) k_normalize_emit<<<grid, 512, 0, stream>>>(x, y, minmax_scratch, fo, sample_count, eps, half, two);
     return cudaGetLastError();
 }
 
