@@ -54,9 +54,6 @@ constexpr uint32_t SV_SMEM_MAX = 224 * 1024;        // + the static barriers sta
 __device__ __forceinline__ float sv_key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
-__device__ __forceinline__ void sv_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 // the single-lane roles address their barriers by 32-bit shared address (formed once, outside the loops)
 __device__ __forceinline__ void sv_wait_u32(uint32_t bar, uint32_t parity) {
     uint32_t ok, spins = 0;
@@ -132,8 +129,6 @@ __device__ __forceinline__ int sv_group_steps(const SpecBranchDev& br, int m, in
     return (m < br.split ? br.blocks : br.blocks - 1) + (m == groups - 1 ? br.pad : 0);
 }
 
-// index of the first K step of pair m in the packed basis
-__device__ __forceinline__ int sv_group_first(const SpecBranchDev& br, int m) { return m * (br.blocks - 1) + min(m, br.split); }
 // Order of the column pairs: the same for every CTA (a per-CTA rotation was tried to spread the basis reads over L2 — no
 // effect on time, and it would make a segment's bits depend on its position in the batch).
 __device__ __forceinline__ int sv_rot(const SpecV24Params&, int) { return 0; }
@@ -245,32 +240,23 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
         __syncwarp();
     } else if (warp == 1) {
         // ================================ loader: basis ring, two K steps per slot ================================
-        // (the packed basis is walked group by group in this CTA's rotated order; a slot may straddle two groups)
+        // One 12 KB bulk copy per slot; the packed basis is already in issue order.  The bulk-copy engine delivers ~27 B/clk
+        // into an SM while the MMAs could consume 43 B/clk: this stream is what the control lane waits for most (35 % of the
+        // kernel).  Tried: the second K step of each slot by 16-byte cp.async from this warp's 32 lanes (LSU path, completion
+        // through cp.async.mbarrier.arrive.noinc) - one warp's cp.async stream is latency-bound (700 cycles per slot), slower.
         if (elect_one()) {
             const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0])), ring0 = sv_opaque(smem_u32(wring));
-            uint32_t st = 0, wph = 1, half = 0;
+            const uint32_t slot_bytes = 2u * kstep_bytes;
+            uint32_t st = 0, wph = 1;
             SvTile t;
             for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
                 const SpecBranchDev& br = p.br[t.slot];
-                const int groups = (br.kcells + 1) >> 1;
-                const int rot = sv_rot(p, groups);
-                for (int mi = 0; mi < groups; ++mi) {
-                    const int m = mi + rot < groups ? mi + rot : mi + rot - groups;
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(br.wpack) + (size_t)sv_group_first(br, m) * kstep_bytes;
-                    int left = sv_group_steps(br, m, groups);
-                    while (left > 0) {
-                        // as many K steps as are contiguous in the packed basis AND in the slot: 1 or 2
-                        const int n = (half == 0 && left >= 2) ? 2 : 1;
-                        if (half == 0) {
-                            sv_wait1<PROF>(we0 + 8u * st, wph, pc0);
-                            sv_expect_tx(wf0 + 8u * st, 2u * kstep_bytes);
-                        }
-                        sv_bulk_g2s(ring0 + (2u * st + half) * kstep_bytes, src, (uint32_t)n * kstep_bytes, wf0 + 8u * st);
-                        src += (size_t)n * kstep_bytes;
-                        left -= n;
-                        half += (uint32_t)n;
-                        if (half == 2) { half = 0; if (++st == NS) { st = 0; wph ^= 1u; } }
-                    }
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(br.wpack);
+                for (int s2 = 0; s2 < (br.n_ksteps >> 1); ++s2, src += slot_bytes) {
+                    sv_wait1<PROF>(we0 + 8u * st, wph, pc0);
+                    sv_expect_tx(wf0 + 8u * st, slot_bytes);
+                    sv_bulk_g2s(ring0 + st * slot_bytes, src, slot_bytes, wf0 + 8u * st);
+                    if (++st == NS) { st = 0; wph ^= 1u; }
                 }
             }
             if (prof) { p.prof[9] = pc0; p.prof[10] = (unsigned long long)(clock64() - t_begin); }
@@ -487,7 +473,7 @@ bool spec_v24_layout(const SpecBranchHost* br, int n_br, int& row_pitch, uint32_
         if (n_pad && n_pad != br[i].n_pad) return false;
         n_pad = br[i].n_pad;
     }
-    row_pitch = (rows + 7) / 8 * 8;
+    row_pitch = rows;                                       // any pitch works (cells are 16 bytes); exact rows leave room for one more ring slot
     patch_plane = (uint32_t)cols * (uint32_t)row_pitch * 16u;
     const uint32_t stage = 128u * (uint32_t)n_pad;           // a ring slot = two K steps
     const uint32_t fixed = 2u * patch_plane + 128u;

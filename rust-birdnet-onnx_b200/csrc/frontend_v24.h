@@ -28,7 +28,7 @@ struct SpecV24Params {
     int row_pitch, n_stages;
     uint32_t patch_plane;
     float eps, half, two;
-    int debug;                // development experiments (BN_FE_DEBUG bits), 0 in production
+    int debug;                // development experiments (BN_FE_DEBUG: 1 = producers write nothing, 256 = no L2 prefetch), 0 in production
     unsigned long long* prof; // optional [16] role cycle counters of CTA 0 (development aid, BN_FE_PROFILE), or nullptr
 };
 
