@@ -1,6 +1,11 @@
 #!/bin/bash
 # 8-GPU box: staging roofline, C-driver e2e (no Python), pool (cfg5 shape), torchrun bench cfg5 and cfg2
 O=gpurun_out/${1:-multi8}; mkdir -p $O
+N=${2:-8}
+python -c "
+import sys; sys.path.insert(0,'rust-birdnet-onnx_b200')
+from birdnet_b200.modelgen.make_models import ensure_model
+ensure_model('birdnet_v24')"
 nvidia-smi -L > $O/gpus.txt; nproc >> $O/gpus.txt; lscpu | grep -E "Model name|Socket|NUMA node\(s\)|^CPU\(s\)" >> $O/gpus.txt; free -g | head -2 >> $O/gpus.txt
 nvidia-smi topo -m > $O/topo.txt 2>&1
 timeout 300 tools/_build/pcie_bench > $O/pcie_bench_8gpu.json 2> $O/pcie_bench.err; cat $O/pcie_bench_8gpu.json
@@ -17,7 +22,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --mast
 for f in cfg5 cfg2; do python - <<PY
 import json
 try:
-    d=json.load(open("$O/bench_${f}_8gpu.json"))
+    d=json.loads(open("$O/bench_${f}_8gpu.json").read().strip().splitlines()[-1])
     print("$f N=8: value %.0f e2e %.0f pageable %.0f ingest %s" % (d["value"], d["e2e"]["value"], d["e2e_pageable"]["value"], d["ingest_pcm16"] and round(d["ingest_pcm16"]["value"])))
 except Exception as e: print("$f failed", e)
 PY

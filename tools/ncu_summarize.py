@@ -5,7 +5,7 @@ reports as roofline.traffic.
     python tools/ncu_summarize.py gpurun_out/r01_ncu_full_raw.csv gpurun_out/stagesNN.log r01
 
 The stage log (PROFILE=1 tools/run_once.py) gives the stage order; launches map to stages in order
-(normalize = 3 launches, every other stage = 1)."""
+(normalize = 2 launches with the fused front-end, 3 with the round-1 path; every other stage = 1)."""
 import csv, json, os, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,8 +36,9 @@ for line in open(stage_log):
             continue
         stages.append(p[0])
 launch_stage = []
+n_norm = 2 if "spectrogram" in stages else 3      # fused front-end: min/max init + pass; round-1 path: + k_normalize_emit
 for s in stages:
-    launch_stage += [s] * (3 if s == "normalize" else 1)
+    launch_stage += [s] * (n_norm if s == "normalize" else 1)
 
 out_rows, traffic = [], {}
 t_unit = units[col["gpu__time_duration.sum"]]
