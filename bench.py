@@ -345,11 +345,20 @@ def _stage_roofline(spec, stage_times, batch, peaks):
             # algorithmic bytes: audio read once (shared by both branches: counted half each) + spectrogram written once
             per = sum(fe.sample_count * 4 / len(fe.specs) + sp.n_mels * sp.n_frames(fe.sample_count) * 4 for sp in specs)
             fl = sum(2.0 * sp.n_frames(fe.sample_count) * sp.n_fft * sp.n_mels for sp in specs)
-            # the FP32-equivalent policy runs three fp16 products per MAC (hi*hi, hi*lo, lo*hi): that is the kernel's own floor
-            d.update(bound="hbm", achieved=per * batch / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
-                     alg_per_segment=per, tensor_equiv_tflops=fl * batch / (ms * 1e-3) / 1e12,
-                     ceilings_ms={"hbm": per * batch / (peaks["hbm"] * 1e9) * 1e3,
-                                  "tensor_3_products": 3.0 * fl * batch / (peaks["tf_sust"] * 1e12) * 1e3})
+            # bound = whichever is slower at peak: the contraction on the tensor pipe or the audio + spectrogram bytes through
+            # HBM.  `achieved` counts the ALGORITHMIC flops (2 per MAC); the FP32-equivalent policy issues three fp16
+            # products per MAC (hi*hi, hi*lo, lo*hi), which `frac_counting_3_products` shows.
+            t_hbm = per * batch / (peaks["hbm"] * 1e9)
+            t_tensor = fl * batch / (peaks["tf_sust"] * 1e12)
+            ceil = {"hbm": t_hbm * 1e3, "tensor": t_tensor * 1e3, "tensor_3_products": 3.0 * t_tensor * 1e3}
+            if t_tensor >= t_hbm:
+                ach = fl * batch / (ms * 1e-3) / 1e12
+                d.update(bound="tensor", achieved=ach, peak=peaks["tf_sust"], unit="TFLOP/s", alg_per_segment=fl,
+                         products_per_mac=3, frac_counting_3_products=3.0 * ach / peaks["tf_sust"],
+                         hbm_gbs=per * batch / (ms * 1e-3) / 1e9, alg_bytes_per_segment=per, ceilings_ms=ceil)
+            else:
+                d.update(bound="hbm", achieved=per * batch / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                         alg_per_segment=per, tensor_equiv_tflops=fl * batch / (ms * 1e-3) / 1e12, ceilings_ms=ceil)
         elif name == "logmel":
             sp = fe.specs[0]
             per = fe.sample_count * 4 + fe.n_frames() * sp.n_mels * 4      # audio read once + spectrogram written once
@@ -661,7 +670,11 @@ def run_ours(args):
                     "kernel": dom["stage"], "kernel_ms": dom["ms"],
                     "share_of_step": dom["share"], "peak_source": peaks["src"] + (" sustained" if dom["bound"] == "tensor" else ""),
                     "algorithmic_per_segment": dom["alg_per_segment"],
+                    "algorithmic_flops_per_launch": (dom["alg_per_segment"] * B if dom["bound"] == "tensor" else None),
                     "dominant_class": classes[0] if classes else None}
+            for k in ("products_per_mac", "frac_counting_3_products", "ceilings_ms"):
+                if k in dom:
+                    roof[k] = dom[k]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
