@@ -29,24 +29,30 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// One Stockham stage of radix R over F interleaved transforms of length M.
+constexpr int LM_TPF = LM_THREADS / LM_FRAMES;       // threads that work on one frame (64): frame = tid / 64, no division by
+                                                     // run-time lengths anywhere in the loops below
+
+// One Stockham stage of radix R over the CTA's frames (transforms of length M, one per 64 threads).
 //   x[j + r*M/R] * W^(r * (j % Ns))  -> R-point DFT ->  y[(j / Ns) * Ns * R + j % Ns + r * Ns]
-// tw[m] = exp(-2*pi*i*m / (2M)); W_(Ns*R)^q = tw[q * (2M / (Ns*R))].
-template <int R>
-__device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, float2* __restrict__ y,
-                                               const float2* __restrict__ tw, int M, int Ns, int F) {
+// tws = this stage's own twiddles [R-1][Ns] (W_(Ns*R)^(r*k), contiguous in k: conflict-free 64-bit reads; the strided
+// reads of the full table were 8- to 16-way bank conflicts); tw = the full table exp(-2*pi*i*m / (2M)) for the R = 3 / 5
+// butterflies.  POW2: Ns is a power of two (always true unless two odd radices follow each other).
+template <int R, bool POW2>
+__device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tws,
+                                               const float2* __restrict__ tw, int M, int Ns, int ns_shift, int F) {
     const int nb = M / R;
-    const int tstep = (2 * M) / (Ns * R);
-    for (int w = threadIdx.x; w < nb * F; w += LM_THREADS) {
-        const int f = w / nb, j = w - f * nb;
-        const float2* xf = x + f * M;
-        float2* yf = y + f * M;
-        const int k = j % Ns;
+    const int f = threadIdx.x / LM_TPF;
+    if (f >= F) return;
+    const float2* xf = x + f * M;
+    float2* yf = y + f * M;
+    for (int j = threadIdx.x % LM_TPF; j < nb; j += LM_TPF) {
+        const int k = POW2 ? (j & (Ns - 1)) : (j % Ns);
+        const int jq = POW2 ? (j >> ns_shift) : (j / Ns);
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             v[r] = xf[j + r * nb];
-            if (r > 0 && Ns > 1) v[r] = cmul(v[r], tw[r * k * tstep]);
+            if (r > 0 && Ns > 1) v[r] = cmul(v[r], tws[(r - 1) * Ns + k]);
         }
         float2 o[R];
         if (R == 2) {
@@ -75,35 +81,65 @@ __device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, flo
                 o[q] = s;
             }
         }
-        const int d0 = (j / Ns) * Ns * R + k;
+        const int d0 = jq * Ns * R + k;
 #pragma unroll
         for (int r = 0; r < R; ++r) yf[d0 + r * Ns] = o[r];
     }
 }
 
+template <int R>
+__device__ __forceinline__ void stockham_dispatch(const float2* x, float2* y, const float2* tws, const float2* tw, int M, int Ns, int F) {
+    if ((Ns & (Ns - 1)) == 0) stockham_stage<R, true>(x, y, tws, tw, M, Ns, 31 - __clz(Ns), F);
+    else stockham_stage<R, false>(x, y, tws, tw, M, Ns, 0, F);
+}
+
 __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
     extern __shared__ __align__(16) unsigned char lm_smem[];
     const int N = p.n_fft, M = N >> 1;
-    float2* tw = reinterpret_cast<float2*>(lm_smem);             // [N]
-    float2* buf0 = tw + N;                                       // [LM_FRAMES][M]
+    float2* tw = reinterpret_cast<float2*>(lm_smem);             // [N]   full table
+    float2* tws = tw + N;                                        // [M]   per-stage tables, stage with stride Ns at offset Ns - 1
+    float2* buf0 = tws + M;                                      // [LM_FRAMES][M]
     float2* buf1 = buf0 + LM_FRAMES * M;                         // [LM_FRAMES][M]
     for (int i = threadIdx.x; i < N; i += LM_THREADS) tw[i] = p.twiddle[i];
+    {
+        int Ns = 1;
+        for (int st = 0; st < p.n_stages; ++st) {
+            const int R = p.radix[st];
+            const int tstep = (2 * M) / (Ns * R);
+            // sum over earlier stages of Ns' * (R' - 1) telescopes to Ns - 1
+            for (int i = threadIdx.x; i < Ns * (R - 1); i += LM_THREADS) {
+                const int r = i / Ns + 1, k = i - (r - 1) * Ns;
+                tws[Ns - 1 + i] = p.twiddle[r * k * tstep];
+            }
+            Ns *= R;
+        }
+    }
     const int b = blockIdx.y;
     const float* xs = p.audio + (size_t)b * p.sample_count;
     const int bins = M + 1;
+    const int f = threadIdx.x / LM_TPF, l = threadIdx.x % LM_TPF;        // this thread's frame of the pass, lane inside it
     for (int pass = 0; pass < LM_PASSES; ++pass) {
         const int t0 = (blockIdx.x * LM_PASSES + pass) * LM_FRAMES;
         if (t0 >= p.n_frames) break;                             // uniform across the CTA
         const int F = min(LM_FRAMES, p.n_frames - t0);
         __syncthreads();                                         // twiddles staged / previous pass consumed
         // windowed frames, even samples -> re, odd samples -> im; zero beyond the segment (pad_end)
-        for (int w = threadIdx.x; w < F * M; w += LM_THREADS) {
-            const int f = w / M, n = w - f * M;
-            const int s0 = (t0 + f) * p.hop + 2 * n;
-            float2 v;
-            v.x = s0 < p.sample_count ? __ldg(xs + s0) * __ldg(p.window + 2 * n) : 0.f;
-            v.y = s0 + 1 < p.sample_count ? __ldg(xs + s0 + 1) * __ldg(p.window + 2 * n + 1) : 0.f;
-            buf0[w] = v;
+        if (f < F) {
+            const int fs = (t0 + f) * p.hop;
+            const bool vec = ((fs & 1) == 0) && fs + N <= p.sample_count;        // 8-byte aligned pairs, all inside the segment
+            for (int n = l; n < M; n += LM_TPF) {
+                const int s0 = fs + 2 * n;
+                const float2 wv = __ldg(reinterpret_cast<const float2*>(p.window) + n);
+                float2 v;
+                if (vec) {
+                    const float2 xv = __ldg(reinterpret_cast<const float2*>(xs + s0));
+                    v = make_float2(xv.x * wv.x, xv.y * wv.y);
+                } else {
+                    v.x = s0 < p.sample_count ? __ldg(xs + s0) * wv.x : 0.f;
+                    v.y = s0 + 1 < p.sample_count ? __ldg(xs + s0 + 1) * wv.y : 0.f;
+                }
+                buf0[f * M + n] = v;
+            }
         }
         __syncthreads();
         float2* src = buf0;
@@ -111,48 +147,52 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
         int Ns = 1;
         for (int st = 0; st < p.n_stages; ++st) {
             const int R = p.radix[st];
-            if (R == 4) stockham_stage<4>(src, dst, tw, M, Ns, F);
-            else if (R == 2) stockham_stage<2>(src, dst, tw, M, Ns, F);
-            else if (R == 5) stockham_stage<5>(src, dst, tw, M, Ns, F);
-            else stockham_stage<3>(src, dst, tw, M, Ns, F);
+            const float2* ts = tws + (Ns - 1);
+            if (R == 4) stockham_dispatch<4>(src, dst, ts, tw, M, Ns, F);
+            else if (R == 2) stockham_dispatch<2>(src, dst, ts, tw, M, Ns, F);
+            else if (R == 5) stockham_dispatch<5>(src, dst, ts, tw, M, Ns, F);
+            else stockham_dispatch<3>(src, dst, ts, tw, M, Ns, F);
             Ns *= R;
             __syncthreads();
             float2* t = src; src = dst; dst = t;
         }
         // |X[k]|, k = 0..M, into the free buffer as float mag[f][bins]
         float* mag = reinterpret_cast<float*>(dst);              // F * (M + 1) floats <= F * M float2
-        for (int w = threadIdx.x; w < F * bins; w += LM_THREADS) {
-            const int f = w / bins, k = w - f * bins;
-            const float2 z = src[f * M + (k == M ? 0 : k)];
-            const float2 zc = src[f * M + (k == 0 || k == M ? 0 : M - k)];
-            const float er = 0.5f * (z.x + zc.x), ei = 0.5f * (z.y - zc.y);     // E[k]
-            const float orr = 0.5f * (z.y + zc.y), oi = -0.5f * (z.x - zc.x);   // O[k] = -i (Z - conj Zc) / 2
-            const float2 wk = tw[k];
-            const float xr = er + (orr * wk.x - oi * wk.y);
-            const float xi = ei + (orr * wk.y + oi * wk.x);
-            mag[w] = sqrtf(xr * xr + xi * xi);
+        if (f < F) {
+            const float2* zf = src + f * M;
+            for (int k = l; k < bins; k += LM_TPF) {
+                const float2 z = zf[k == M ? 0 : k];
+                const float2 zc = zf[k == 0 || k == M ? 0 : M - k];
+                const float er = 0.5f * (z.x + zc.x), ei = 0.5f * (z.y - zc.y);     // E[k]
+                const float orr = 0.5f * (z.y + zc.y), oi = -0.5f * (z.x - zc.x);   // O[k] = -i (Z - conj Zc) / 2
+                const float2 wk = tw[k];
+                const float xr = er + (orr * wk.x - oi * wk.y);
+                const float xi = ei + (orr * wk.y + oi * wk.x);
+                mag[f * bins + k] = sqrtf(xr * xr + xi * xi);
+            }
         }
         __syncthreads();
-        for (int w = threadIdx.x; w < F * p.n_mels; w += LM_THREADS) {
-            const int f = w / p.n_mels, m = w - f * p.n_mels;
-            const int lo = __ldg(p.mel_lo + m), cnt = __ldg(p.mel_cnt + m);
-            const float* wt = p.mel_w + __ldg(p.mel_off + m);
-            const float* mg = mag + f * bins + lo;
-            float s = 0.f;
-            for (int i = 0; i < cnt; ++i) s = fmaf(mg[i], __ldg(wt + i), s);
-            const float y = p.log_scale * logf(s + p.log_floor);
-            const size_t o = ((size_t)b * p.n_frames + t0 + f) * p.n_mels + m;
-            const __half h = __float2half_rn(y);
-            p.out.hi[o] = h;
-            p.out.hi[p.out.plane + o] = __float2half_rn(y - __half2float(h));
-            if (p.out_f32) p.out_f32[o] = y;
+        if (f < F) {
+            for (int m = l; m < p.n_mels; m += LM_TPF) {
+                const int lo = __ldg(p.mel_lo + m), cnt = __ldg(p.mel_cnt + m);
+                const float* wt = p.mel_w + __ldg(p.mel_off + m);
+                const float* mg = mag + f * bins + lo;
+                float s = 0.f;
+                for (int i = 0; i < cnt; ++i) s = fmaf(mg[i], __ldg(wt + i), s);
+                const float y = p.log_scale * logf(s + p.log_floor);
+                const size_t o = ((size_t)b * p.n_frames + t0 + f) * p.n_mels + m;
+                const __half h = __float2half_rn(y);
+                p.out.hi[o] = h;
+                p.out.hi[p.out.plane + o] = __float2half_rn(y - __half2float(h));
+                if (p.out_f32) p.out_f32[o] = y;
+            }
         }
     }
 }
 
 }  // namespace
 
-size_t logmel_smem_bytes(int n_fft) { return (size_t)(n_fft + 2 * LM_FRAMES * (n_fft / 2)) * sizeof(float2); }
+size_t logmel_smem_bytes(int n_fft) { return (size_t)(n_fft + n_fft / 2 + 2 * LM_FRAMES * (n_fft / 2)) * sizeof(float2); }
 
 bool logmel_factorize(int n_fft, int radix[8], int* n_stages) {
     if (n_fft < 8 || (n_fft & 1)) return false;
