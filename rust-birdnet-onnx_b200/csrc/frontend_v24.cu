@@ -499,3 +499,77 @@ cudaError_t launch_spec_v24(const SpecV24Params& p, uint32_t smem_bytes, int num
 }
 
 }  // namespace bn
+
+// Host-only self check of the K-step schedule and the packed basis (development symbol, not part of include/birdnet_b200.h;
+// tests/test_frontend_v24_host.py calls it on CPU): for a deterministic pseudo-random signal and basis, the sum over the
+// schedule - patch cells addressed exactly as the kernel's descriptors address them (cell column, row shift, LBO = one
+// column) times the packed hi + lo weights - against the direct dot product, in double.  Returns the worst difference;
+// out[0..2] = K steps, ring slots, shared-memory bytes of the plan.  -1 = shape not covered by the kernel.
+extern "C" double bn_debug_spec_v24_selfcheck(int n_fft, int hop, int n_mels, int sample_count, int* out) {
+    using namespace bn;
+    SpecBranchHost hb;
+    if (!spec_v24_plan(n_fft, hop, n_mels, hb)) return -1.0;
+    int rp = 0, ns = 0;
+    uint32_t plane = 0, smem = 0;
+    if (!spec_v24_layout(&hb, 1, rp, plane, ns, smem)) return -1.0;
+    if (out) { out[0] = (int)hb.table.size(); out[1] = ns; out[2] = (int)smem; }
+    const int ldb = (n_mels + 3) / 4 * 4, N = hb.n_pad, S = sample_count;
+    const int T = 1 + (S - n_fft) / hop;
+    std::vector<float> x((size_t)S), basis((size_t)n_fft * ldb);
+    uint32_t lcg = 12345u;
+    auto rnd = [&]() { lcg = lcg * 1664525u + 1013904223u; return (float)((lcg >> 8) & 0xffff) / 65536.f - 0.5f; };
+    for (auto& v : x) v = rnd();
+    for (auto& v : basis) v = rnd() * 0.25f;
+    std::vector<uint16_t> pack;
+    spec_v24_pack(hb, basis.data(), ldb, n_fft, n_mels, pack);
+    // the device's own enumeration (column pair outer, blocks inner, zero step at the end of the last pair)
+    std::vector<uint32_t> cell0;
+    const int groups = (hb.kcells + 1) / 2;
+    for (int m = 0; m < groups; ++m) {
+        const int jn = (m < hb.split ? hb.blocks : hb.blocks - 1) + (m == groups - 1 ? hb.pad : 0);
+        for (int j = 0; j < jn; ++j) cell0.push_back((uint32_t)(2 * m) * (uint32_t)rp + (uint32_t)j);
+    }
+    if (cell0.size() != hb.table.size()) return 1e30;
+    const int cols = (hb.kcells + 1) / 2 * 2;
+    double worst = 0.0;
+    const int tiles = (T + 127) / 128;
+    const int t0s[3] = {0, 128 * (tiles / 2), 128 * (tiles - 1)};
+    for (int ti = 0; ti < 3; ++ti) {
+        const int t0 = t0s[ti];
+        std::vector<float> patch((size_t)cols * rp * 8, 0.f);
+        for (int c = 0; c < hb.kcells; ++c)
+            for (int r = 0; r < hb.rows; ++r)
+                for (int i = 0; i < 8; ++i) {
+                    const long long sidx = (long long)(t0 + r) * hop + c * 8 + i;
+                    patch[((size_t)c * rp + r) * 8 + i] = sidx < S ? x[(size_t)sidx] : 0.f;
+                }
+        const int rows_i[5] = {0, 1, 63, 126, 127};
+        const int mels[3] = {0, n_mels / 2, n_mels - 1};
+        for (int ri = 0; ri < 5; ++ri) {
+            const int i = rows_i[ri], t = t0 + i;
+            if (t >= T) continue;
+            for (int mi = 0; mi < 3; ++mi) {
+                const int mel = mels[mi];
+                double acc = 0.0;
+                for (size_t ks = 0; ks < cell0.size(); ++ks) {
+                    const uint16_t* w = pack.data() + ks * (size_t)(2 * 2 * N * 8);
+                    for (int kc = 0; kc < 2; ++kc)
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const float a = patch[((size_t)cell0[ks] + (size_t)kc * rp + i) * 8 + kk];
+                            const float wv = sv_h2f(w[((size_t)kc * 2 * N + mel) * 8 + kk]) + sv_h2f(w[((size_t)kc * 2 * N + N + mel) * 8 + kk]);
+                            acc += (double)a * (double)wv;
+                        }
+                }
+                double ref = 0.0;
+                for (int n = 0; n < n_fft; ++n) {
+                    const float wq = basis[(size_t)n * ldb + mel];
+                    const uint16_t h = sv_f2h(wq);
+                    ref += (double)x[(size_t)t * hop + n] * ((double)sv_h2f(h) + (double)sv_h2f(sv_f2h(wq - sv_h2f(h))));
+                }
+                worst = std::max(worst, fabs(acc - ref));
+            }
+        }
+    }
+    return worst;
+}
+
