@@ -75,6 +75,15 @@ __device__ __forceinline__ void sv_wait1(uint32_t bar, uint32_t parity, unsigned
     sv_wait_u32(bar, parity);
     acc += (unsigned long long)(clock64() - t0);
 }
+// registers -> TMEM: lane i of the warp -> TMEM lane base+i, 16 consecutive 32-bit columns (the mirror of tmem_ld16)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // keeps an address the compiler would otherwise re-derive (S2UR SR_CgaCtaId + ULEA per use) in a register
 __device__ __forceinline__ uint32_t sv_opaque(uint32_t v) {
     uint32_t r;
@@ -101,22 +110,33 @@ __device__ __forceinline__ void sv_wait(uint64_t* bar, uint32_t parity, unsigned
 
 extern __shared__ __align__(16) uint8_t sv_smem_raw[];
 
-// tile n of this CTA -> (branch slot, segment, first frame).  Slot 0 (the longer K loop) is dealt round-robin from CTA 0
-// up, slot 1 from the last CTA down, so a CTA that got one more long tile gets one fewer short tile.
+// tile n of this CTA -> (branch slot, segment, first frame).
+// Paired order (two branches whose results fit the TMEM stash): the CTA runs both branches of the same 128 frames back
+// to back - slot 0, then slot 1 - so the second read of the audio range hits L2 and the epilogue can write both channels
+// of a spectrogram pixel as one 32-bit word (full 32-byte sectors instead of every other 2 bytes).
+// Unpaired order: slot 0 (the longer K loop) is dealt round-robin from CTA 0 up, slot 1 from the last CTA down, so a CTA
+// that got one more long tile gets one fewer short tile.
 struct SvTile { int slot, seg, t0; };
+__device__ __forceinline__ bool sv_paired(const SpecV24Params& p) { return p.n_br == 2 && 5 * p.n_pad <= 512 && p.n_ch == 2; }
 __device__ __forceinline__ bool sv_tile(const SpecV24Params& p, int n, SvTile& t) {
     const int grid = (int)gridDim.x, bx = (int)blockIdx.x;
     const int per = p.batch * p.tiles_per_seg;
-    const int mine0 = bx < per ? (per - 1 - bx) / grid + 1 : 0;
     int idx;
-    if (n < mine0) {
-        t.slot = 0;
-        idx = bx + n * grid;
-    } else {
-        if (p.n_br < 2) return false;
-        t.slot = 1;
-        idx = (grid - 1 - bx) + (n - mine0) * grid;
+    if (sv_paired(p)) {
+        t.slot = n & 1;
+        idx = bx + (n >> 1) * grid;
         if (idx >= per) return false;
+    } else {
+        const int mine0 = bx < per ? (per - 1 - bx) / grid + 1 : 0;
+        if (n < mine0) {
+            t.slot = 0;
+            idx = bx + n * grid;
+        } else {
+            if (p.n_br < 2) return false;
+            t.slot = 1;
+            idx = (grid - 1 - bx) + (n - mine0) * grid;
+            if (idx >= per) return false;
+        }
     }
     t.seg = idx / p.tiles_per_seg;
     t.t0 = (idx - t.seg * p.tiles_per_seg) * 128;
@@ -266,6 +286,9 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
         // ================================ epilogue ================================
         const uint32_t q = (uint32_t)warp & 3u;                 // TMEM lane quarter this warp may read
         const uint32_t par = (uint32_t)(warp - 2) >> 2;         // which of the alternating 16-column chunks
+        const bool paired = sv_paired(p);
+        const uint32_t stash = tmem_base + ((q * 32u) << 16) + 4u * N;      // N spare TMEM columns behind the two accumulator sets
+        const bool first_is_ch0 = p.br[0].ch == 0;
         SvTile t;
         for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
             const SpecBranchDev& br = p.br[t.slot];
@@ -276,28 +299,41 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
             const bool row_ok = tt < p.n_frames;
             const uint32_t t_lane = tmem_base + ((q * 32u) << 16) + as * 2u * N;
             const size_t mel_stride = (size_t)p.n_frames * p.n_ch;
-            __half* out = p.out_hi + ((size_t)t.seg * p.n_mels * p.n_frames + (size_t)tt) * p.n_ch + br.ch;
+            const size_t pix = ((size_t)t.seg * p.n_mels * p.n_frames + (size_t)tt) * p.n_ch;
             const float ex = br.exponent;
             for (uint32_t c0 = par * 16u; c0 < N; c0 += 16u * (SV_EPI_WARPS / 4)) {
-                uint32_t rm[16], rc[16];
+                uint32_t rm[16], rc[16], pk[16];
                 tmem_ld16_nowait(t_lane + c0, rm);
                 tmem_ld16_nowait(t_lane + N + c0, rc);
+                if (paired && t.slot == 1) tmem_ld16_nowait(stash + c0, pk);      // the other branch's hi | lo << 16 of the same pixels
                 tmem_ld_wait();
-                if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if ((int)c0 + j < p.n_mels) {
-                            const float v = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
-                            const float pw = v * v;
-                            const float r = pw > 0.f ? exp2f(ex * __log2f(pw)) : pw;
-                            __half* o = out + (size_t)(c0 + j) * mel_stride;
-                            const __half hh = __float2half_rn(r);
+                for (int j = 0; j < 16; ++j) {
+                    const float v = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+                    const float pw = v * v;
+                    const float r = pw > 0.f ? exp2f(ex * __log2f(pw)) : pw;
+                    const __half hh = __float2half_rn(r);
+                    const __half ll = __float2half_rn(r - __half2float(hh));
+                    const uint32_t mine = (uint32_t)__half_as_ushort(hh) | ((uint32_t)__half_as_ushort(ll) << 16);
+                    if (!paired) {
+                        if (row_ok && (int)c0 + j < p.n_mels) {
+                            __half* o = p.out_hi + pix + br.ch + (size_t)(c0 + j) * mel_stride;
                             o[0] = hh;
-                            o[p.out_plane] = __float2half_rn(r - __half2float(hh));
+                            o[p.out_plane] = ll;
                         }
+                    } else if (t.slot == 0) {
+                        pk[j] = mine;
+                    } else if (row_ok && (int)c0 + j < p.n_mels) {
+                        const uint32_t c_first = pk[j], c_second = mine;        // slot 0's branch, slot 1's branch
+                        const uint32_t a0 = first_is_ch0 ? c_first : c_second, a1 = first_is_ch0 ? c_second : c_first;
+                        uint32_t* o = reinterpret_cast<uint32_t*>(p.out_hi + pix + (size_t)(c0 + j) * mel_stride);
+                        o[0] = (a0 & 0xFFFFu) | (a1 << 16);                                 // hi plane: channel 0 | channel 1
+                        o[p.out_plane >> 1] = (a0 >> 16) | (a1 & 0xFFFF0000u);              // lo plane
                     }
                 }
+                if (paired && t.slot == 0) tmem_st16(stash + c0, pk);
             }
+            if (paired && t.slot == 0) tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
