@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #ifndef SV_SPIN_WAIT
@@ -93,6 +94,24 @@ __device__ __forceinline__ uint32_t sv_opaque(uint32_t v) {
 __device__ __forceinline__ void sv_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// cluster forms: the commit arrives on the barrier at the same offset in every CTA of the mask, the bulk copy lands in
+// every CTA of the mask (same offsets) and completes bytes on each one's barrier
+__device__ __forceinline__ void sv_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void sv_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void sv_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t sv_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void sv_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -153,7 +172,13 @@ __device__ __forceinline__ int sv_group_steps(const SpecBranchDev& br, int m, in
 // effect on time, and it would make a segment's bits depend on its position in the batch).
 __device__ __forceinline__ int sv_rot(const SpecV24Params&, int) { return 0; }
 
-template <bool PROF>
+// CL (opt-in, BN_FE_CLUSTER=1): launched as clusters of two CTAs that share the basis stream - each loader fetches every
+// other ring slot and multicasts it into both CTAs' rings (half the bulk-copy bytes per SM, half the L2 -> SM traffic); a
+// slot is free again when BOTH control lanes' MMAs on it have completed (their commits arrive on both CTAs' barriers).
+// Both CTAs of a pair always have the same number of tiles (tiles per segment is even), so they walk identical slot
+// sequences.  Measured: bit-identical results and the same 0.31 ms as the plain launch - the control lane's wait for basis
+// slots is not a bandwidth limit of the bulk-copy engine, so the plain launch stays the default.
+template <bool PROF, bool CL>
 __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params p) {
     __shared__ __align__(8) uint64_t g_full[SV_MAX_GROUPS];     // patch column pair written (producer warp -> control)
     __shared__ __align__(8) uint64_t g_empty[SV_MAX_GROUPS];    // its MMAs completed (tcgen05.commit -> producers)
@@ -175,7 +200,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
 
     if (tid == 0) {
         for (int i = 0; i < SV_MAX_GROUPS; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
-        for (int i = 0; i < SV_MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < SV_MAX_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], CL ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], SV_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -201,6 +226,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL) sv_cluster_sync();                                  // the peer's barriers exist before anything arrives on them
     const uint32_t tmem_base = tmem_holder;
     // development aid (PROF): cycles of CTA 0.  control [0] wait accumulator free [1] wait patch columns [2] wait basis step
     // [3] total [4] tiles | producer warp 0: [5] wait columns free [6] total | epilogue warp 0: [7] wait MMAs [8] total |
@@ -248,7 +274,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
                     umma_f16(acc, da_hi0 + (uint64_t)(e.y & 0xFFFFu), db + step16, idesc2, 1u);
                     umma_f16(acc + N, da_lo0 + (uint64_t)(e.y & 0xFFFFu), db + step16, idesc1, 1u);
                     if (e.y & SV_LAST) sv_commit(ge0 + ((e.y >> 13) & 0x7F8u));
-                    sv_commit(we0 + 8u * st);
+                    if (CL) sv_commit_mc(we0 + 8u * st, (uint16_t)3); else sv_commit(we0 + 8u * st);
                     accum = 1u;
                     if (++st == NS) { st = 0; wph ^= 1u; }
                 }
@@ -267,15 +293,17 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
         if (elect_one()) {
             const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0])), ring0 = sv_opaque(smem_u32(wring));
             const uint32_t slot_bytes = 2u * kstep_bytes;
-            uint32_t st = 0, wph = 1;
+            const uint32_t rank = CL ? sv_cluster_rank() : 0u;
+            uint32_t st = 0, wph = 1, seq = 0;
             SvTile t;
             for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
                 const SpecBranchDev& br = p.br[t.slot];
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(br.wpack);
-                for (int s2 = 0; s2 < (br.n_ksteps >> 1); ++s2, src += slot_bytes) {
+                for (int s2 = 0; s2 < (br.n_ksteps >> 1); ++s2, src += slot_bytes, ++seq) {
                     sv_wait1<PROF>(we0 + 8u * st, wph, pc0);
                     sv_expect_tx(wf0 + 8u * st, slot_bytes);
-                    sv_bulk_g2s(ring0 + st * slot_bytes, src, slot_bytes, wf0 + 8u * st);
+                    if (!CL) sv_bulk_g2s(ring0 + st * slot_bytes, src, slot_bytes, wf0 + 8u * st);
+                    else if ((seq & 1u) == rank) sv_bulk_g2s_mc(ring0 + st * slot_bytes, src, slot_bytes, wf0 + 8u * st, (uint16_t)3);
                     if (++st == NS) { st = 0; wph ^= 1u; }
                 }
             }
@@ -434,6 +462,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (CL) sv_cluster_sync();                                  // nobody leaves while the peer may still signal or copy into it
 }
 
 }  // namespace
@@ -519,19 +548,56 @@ bool spec_v24_layout(const SpecBranchHost* br, int n_br, int& row_pitch, uint32_
     return 2 * 2 * n_pad <= 512 && n_stages >= 2;
 }
 
+static int g_sv_cluster = -1;       // -1 unknown, 0 plain launch, 1 clusters of two
+
 cudaError_t spec_v24_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(k_spec_v24<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_spec_v24<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_spec_v24<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_spec_v24<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_spec_v24<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_spec_v24<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_MAX)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+// clusters of two need every pair co-resident: ask the occupancy calculator once (BN_FE_CLUSTER=1 opts in)
+static bool sv_use_cluster(int grid, uint32_t smem_bytes) {
+    if (g_sv_cluster < 0) {
+        const char* ev = getenv("BN_FE_CLUSTER");
+        g_sv_cluster = 0;
+        if (ev && ev[0] == '1') {                           // opt-in: measured equal to the plain launch
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(SV_THREADS); cfg.dynamicSmemBytes = smem_bytes;
+            cudaLaunchAttribute at{};
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_spec_v24<false, true>, &cfg) == cudaSuccess && 2 * n >= grid) g_sv_cluster = 1;
+            else (void)cudaGetLastError();
+        }
+    }
+    return g_sv_cluster == 1;
 }
 
 cudaError_t launch_spec_v24(const SpecV24Params& p, uint32_t smem_bytes, int num_sms, cudaStream_t stream) {
     if (p.batch <= 0) return cudaSuccess;
     const int per = p.batch * p.tiles_per_seg;
     const int grid = std::min(num_sms, per);
-    if (p.prof) k_spec_v24<true><<<grid, SV_THREADS, smem_bytes, stream>>>(p);
-    else k_spec_v24<false><<<grid, SV_THREADS, smem_bytes, stream>>>(p);
-    return cudaGetLastError();
+    // pairs must walk identical slot sequences: an even grid and an even tile count per branch give both CTAs of a pair
+    // the same number of tiles (per - 1 - bx is odd for both, grid is even)
+    const bool cl = (grid % 2 == 0) && (per % 2 == 0) && (grid == num_sms) && sv_use_cluster(grid, smem_bytes);
+    if (!cl) {
+        if (p.prof) k_spec_v24<true, false><<<grid, SV_THREADS, smem_bytes, stream>>>(p);
+        else k_spec_v24<false, false><<<grid, SV_THREADS, smem_bytes, stream>>>(p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(SV_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    return p.prof ? cudaLaunchKernelEx(&cfg, k_spec_v24<true, true>, p) : cudaLaunchKernelEx(&cfg, k_spec_v24<false, true>, p);
 }
 
 }  // namespace bn
