@@ -7,7 +7,8 @@
 // where the DFT-as-GEMM would be 2 MFLOP.  One CTA transforms FRAMES_PER_PASS frames at a time in
 // shared memory:
 //   * real FFT of length N as a complex Stockham FFT of length M = N/2 over z[n] = x[2n] + i x[2n+1]
-//     (mixed radix 2/3/4/5, twiddles from a float64-built table staged in smem),
+//     (mixed radix 8/4/2/5/3, twiddles from a float64-built table staged in smem; frame buffers padded by one
+//     element per 32 against the scatter's bank conflicts),
 //   * split:  X[k] = E[k] + W_N^k O[k],  E = (Z[k] + conj Z[M-k])/2,  O = -i (Z[k] - conj Z[M-k])/2,
 //   * |X[k]| for k = 0..N/2, then the mel projection as a banded sum (each triangular filter is a
 //     contiguous run of bins), log, hi/lo fp16 split, 256-byte coalesced row stores.
@@ -29,6 +30,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+// element i of a frame buffer lives at i + i/32: one pad float2 per 32 breaks the power-of-two strides of the Stockham
+// scatter (stride R * 8 bytes in the first stage: 16-way bank conflicts unpadded, 2-way padded)
+__device__ __forceinline__ int lm_skew(int i) { return i + (i >> 5); }
+__host__ __device__ constexpr int lm_padded(int m) { return m + (m >> 5) + 1; }
+
 constexpr int LM_TPF = LM_THREADS / LM_FRAMES;       // threads that work on one frame (64): frame = tid / 64, no division by
                                                      // run-time lengths anywhere in the loops below
 
@@ -43,21 +49,39 @@ __device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, flo
     const int nb = M / R;
     const int f = threadIdx.x / LM_TPF;
     if (f >= F) return;
-    const float2* xf = x + f * M;
-    float2* yf = y + f * M;
+    const int MP = lm_padded(M);
+    const float2* xf = x + f * MP;
+    float2* yf = y + f * MP;
     for (int j = threadIdx.x % LM_TPF; j < nb; j += LM_TPF) {
         const int k = POW2 ? (j & (Ns - 1)) : (j % Ns);
         const int jq = POW2 ? (j >> ns_shift) : (j / Ns);
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            v[r] = xf[j + r * nb];
+            v[r] = xf[lm_skew(j + r * nb)];
             if (r > 0 && Ns > 1) v[r] = cmul(v[r], tws[(r - 1) * Ns + k]);
         }
         float2 o[R];
         if (R == 2) {
             o[0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
             o[1] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+        } else if (R == 8) {
+            // 8-point DFT: two 4-point DFTs (even / odd inputs) + W8 twiddles; h = 1/sqrt(2)
+            const float h = 0.70710678118654752f;
+            auto add = [](float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); };
+            auto sub = [](float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); };
+            auto mi = [](float2 a) { return make_float2(a.y, -a.x); };                    // -i * a
+            const float2 a0 = add(v[0], v[4]), a1 = sub(v[0], v[4]), a2 = add(v[2], v[6]), a3 = mi(sub(v[2], v[6]));
+            const float2 a4 = add(v[1], v[5]), a5 = sub(v[1], v[5]), a6 = add(v[3], v[7]), a7 = mi(sub(v[3], v[7]));
+            const float2 e0 = add(a0, a2), e2 = sub(a0, a2), e1 = add(a1, a3), e3 = sub(a1, a3);
+            const float2 q0 = add(a4, a6), q2 = sub(a4, a6), q1 = add(a5, a7), q3 = sub(a5, a7);
+            const float2 t1 = make_float2((q1.x + q1.y) * h, (q1.y - q1.x) * h);          // q1 * (1 - i) / sqrt 2
+            const float2 t2 = mi(q2);
+            const float2 t3 = make_float2((q3.y - q3.x) * h, -(q3.x + q3.y) * h);         // q3 * (-1 - i) / sqrt 2
+            o[0] = add(e0, q0); o[4] = sub(e0, q0);
+            o[1] = add(e1, t1); o[5] = sub(e1, t1);
+            o[2] = add(e2, t2); o[6] = sub(e2, t2);
+            o[3] = add(e3, t3); o[7] = sub(e3, t3);
         } else if (R == 4) {
             const float2 a = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
             const float2 b = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
@@ -83,7 +107,7 @@ __device__ __forceinline__ void stockham_stage(const float2* __restrict__ x, flo
         }
         const int d0 = jq * Ns * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) yf[d0 + r * Ns] = o[r];
+        for (int r = 0; r < R; ++r) yf[lm_skew(d0 + r * Ns)] = o[r];
     }
 }
 
@@ -98,8 +122,9 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
     const int N = p.n_fft, M = N >> 1;
     float2* tw = reinterpret_cast<float2*>(lm_smem);             // [N]   full table
     float2* tws = tw + N;                                        // [M]   per-stage tables, stage with stride Ns at offset Ns - 1
-    float2* buf0 = tws + M;                                      // [LM_FRAMES][M]
-    float2* buf1 = buf0 + LM_FRAMES * M;                         // [LM_FRAMES][M]
+    const int MP = lm_padded(M);
+    float2* buf0 = tws + M;                                      // [LM_FRAMES][MP], element i at lm_skew(i)
+    float2* buf1 = buf0 + LM_FRAMES * MP;                        // [LM_FRAMES][MP]
     for (int i = threadIdx.x; i < N; i += LM_THREADS) tw[i] = p.twiddle[i];
     {
         int Ns = 1;
@@ -138,7 +163,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
                     v.x = s0 < p.sample_count ? __ldg(xs + s0) * wv.x : 0.f;
                     v.y = s0 + 1 < p.sample_count ? __ldg(xs + s0 + 1) * wv.y : 0.f;
                 }
-                buf0[f * M + n] = v;
+                buf0[f * MP + lm_skew(n)] = v;
             }
         }
         __syncthreads();
@@ -148,7 +173,8 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
         for (int st = 0; st < p.n_stages; ++st) {
             const int R = p.radix[st];
             const float2* ts = tws + (Ns - 1);
-            if (R == 4) stockham_dispatch<4>(src, dst, ts, tw, M, Ns, F);
+            if (R == 8) stockham_dispatch<8>(src, dst, ts, tw, M, Ns, F);
+            else if (R == 4) stockham_dispatch<4>(src, dst, ts, tw, M, Ns, F);
             else if (R == 2) stockham_dispatch<2>(src, dst, ts, tw, M, Ns, F);
             else if (R == 5) stockham_dispatch<5>(src, dst, ts, tw, M, Ns, F);
             else stockham_dispatch<3>(src, dst, ts, tw, M, Ns, F);
@@ -157,12 +183,12 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
             float2* t = src; src = dst; dst = t;
         }
         // |X[k]|, k = 0..M, into the free buffer as float mag[f][bins]
-        float* mag = reinterpret_cast<float*>(dst);              // F * (M + 1) floats <= F * M float2
+        float* mag = reinterpret_cast<float*>(dst);              // F * (M + 1) floats <= F * MP float2
         if (f < F) {
-            const float2* zf = src + f * M;
+            const float2* zf = src + f * MP;
             for (int k = l; k < bins; k += LM_TPF) {
-                const float2 z = zf[k == M ? 0 : k];
-                const float2 zc = zf[k == 0 || k == M ? 0 : M - k];
+                const float2 z = zf[lm_skew(k == M ? 0 : k)];
+                const float2 zc = zf[lm_skew(k == 0 || k == M ? 0 : M - k)];
                 const float er = 0.5f * (z.x + zc.x), ei = 0.5f * (z.y - zc.y);     // E[k]
                 const float orr = 0.5f * (z.y + zc.y), oi = -0.5f * (z.x - zc.x);   // O[k] = -i (Z - conj Zc) / 2
                 const float2 wk = tw[k];
@@ -172,6 +198,9 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
             }
         }
         __syncthreads();
+        // Mel projection, one thread per filter (a banded dot product).  Sharing a filter between eight lanes (strided
+        // partial sums + shuffles) was measured SLOWER (1.18 -> 1.91 ms): the phase is bound by the latency of the three
+        // per-filter metadata loads, which the shared form repeats eight times as often per lane, not by the MAC count.
         if (f < F) {
             for (int m = l; m < p.n_mels; m += LM_TPF) {
                 const int lo = __ldg(p.mel_lo + m), cnt = __ldg(p.mel_cnt + m);
@@ -192,13 +221,13 @@ __global__ void __launch_bounds__(LM_THREADS) k_logmel(LogmelParams p) {
 
 }  // namespace
 
-size_t logmel_smem_bytes(int n_fft) { return (size_t)(n_fft + n_fft / 2 + 2 * LM_FRAMES * (n_fft / 2)) * sizeof(float2); }
+size_t logmel_smem_bytes(int n_fft) { return (size_t)(n_fft + n_fft / 2 + 2 * LM_FRAMES * lm_padded(n_fft / 2)) * sizeof(float2); }
 
 bool logmel_factorize(int n_fft, int radix[8], int* n_stages) {
     if (n_fft < 8 || (n_fft & 1)) return false;
     int m = n_fft / 2, n = 0;
-    const int cand[4] = {4, 2, 5, 3};
-    for (int ci = 0; ci < 4; ++ci)
+    const int cand[5] = {8, 4, 2, 5, 3};          // largest power-of-two radix first: 512 = 8*8*8, 320 = 8*8*5
+    for (int ci = 0; ci < 5; ++ci)
         while (m % cand[ci] == 0) {
             if (n >= 8) return false;
             radix[n++] = cand[ci];
