@@ -85,6 +85,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// out of line on purpose: the producers call it only for degenerate denominators and must not pay for it otherwise
+__device__ __noinline__ float sv_ieee_div(float a, float b) { return __fdiv_rn(a, b); }
 // keeps an address the compiler would otherwise re-derive (S2UR SR_CgaCtaId + ULEA per use) in a register
 __device__ __forceinline__ uint32_t sv_opaque(uint32_t v) {
     uint32_t r;
@@ -405,39 +407,40 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
                 sv_wait<PROF>(&g_empty[m], (it & 1u) ^ 1u, pc0);
                 uint8_t* col = patch + (size_t)(2 * m) * RP * 16u;          // cells 2m (and 2m + 1, RP cells further)
                 const bool two = 2 * m + 1 < br.kcells;                     // odd cell count: the last pair has one weighted cell
-                if (!(p.debug & 1))
-                for (int r0 = lane; r0 < br.rows; r0 += 64) {
-                    // two rows per pass, every load issued before the first use
+                // normalised value of raw sample x (samples past the segment end are exactly zero)
+                auto norm = [&](float x, bool valid) {
+                    // (x - lo) / den as reciprocal + one residual correction: the IEEE quotient in all but rare half-ulp
+                    // cases at 3 instructions instead of ~18 (the producers were issue-bound); the value is split to 22
+                    // bits right after.  Degenerate denominators (NaN / Inf / denormal range) take the IEEE division.
+                    const float a = __fsub_rn(x, lo);
+                    const float q0 = __fmul_rn(a, rden);
+                    float q = __fmaf_rn(__fmaf_rn(-q0, den, a), rden, q0);
+                    if (!den_ok) q = sv_ieee_div(a, den);
+                    return valid ? __fmul_rn(__fsub_rn(q, p.half), p.two) : 0.f;
+                };
+                const int full = br.rows & ~63;                             // rows the two-row passes cover
+                if (!(p.debug & 1)) {
+                for (int r0 = lane; r0 < full; r0 += 64) {
+                    // two rows per pass (both cells of the pair: 16 samples each), every load issued before the first use
                     float v[2][16];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const int r = r0 + 32 * u;
-                        const int s0 = (t.t0 + r) * br.hop + m * 16;
-                        if (r < br.rows && even_hop && s0 + 16 <= p.S) {
+                        const int s0 = (t.t0 + r0 + 32 * u) * br.hop + m * 16;
+                        if (even_hop && s0 + 16 <= p.S) {
                             const float2* g = reinterpret_cast<const float2*>(xs + s0);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) { const float2 f = __ldg(g + i); v[u][2 * i] = f.x; v[u][2 * i + 1] = f.y; }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[u][i] = (r < br.rows && s0 + i < p.S) ? __ldg(xs + s0 + i) : lo;
+                            for (int i = 0; i < 16; ++i) v[u][i] = s0 + i < p.S ? __ldg(xs + s0 + i) : lo;
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int r = r0 + 32 * u;
-                        if (r >= br.rows) break;
-                        const int nvalid = p.S - ((t.t0 + r) * br.hop + m * 16);     // samples past the segment end stay exactly zero
+                        const int nvalid = p.S - ((t.t0 + r) * br.hop + m * 16);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            // (x - lo) / den as reciprocal + one residual correction: the IEEE quotient in all but rare
-                            // half-ulp cases, at 3 instructions instead of the ~18 of __fdiv_rn (the producers were issue-bound);
-                            // the value is split to 22 bits right after, the FP32 normalised copy the tests read is not made here
-                            const float a = __fsub_rn(v[u][i], lo);
-                            const float q0 = __fmul_rn(a, rden);
-                            const float q = __fmaf_rn(__fmaf_rn(-q0, den, a), rden, q0);
-                            const float xn = __fmul_rn(__fsub_rn(den_ok ? q : __fdiv_rn(a, den), p.half), p.two);
-                            v[u][i] = i < nvalid ? xn : 0.f;
-                        }
+                        for (int i = 0; i < 16; ++i) v[u][i] = norm(v[u][i], i < nvalid);
                         uint4 h, l;
                         split8(v[u], h, l);
                         *reinterpret_cast<uint4*>(col + (size_t)r * 16u) = h;
@@ -451,6 +454,23 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
                         *reinterpret_cast<uint4*>(col + (size_t)(RP + r) * 16u) = h;
                         *reinterpret_cast<uint4*>(col + plane + (size_t)(RP + r) * 16u) = l;
                     }
+                }
+                // the few rows past the last full pass (7 of 135): one (row, cell) item of 8 samples per lane
+                for (int idx = lane; idx < 2 * (br.rows - full); idx += 32) {
+                    const int r = full + (idx >> 1), kc = idx & 1;
+                    const int s0 = (t.t0 + r) * br.hop + m * 16 + kc * 8;
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = s0 + i < p.S ? __ldg(xs + s0 + i) : lo;
+                    const int nvalid = p.S - s0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = norm(v[i], i < nvalid);
+                    uint4 h, l;
+                    split8(v, h, l);
+                    if (kc == 1 && !two) { h = make_uint4(0u, 0u, 0u, 0u); l = h; }
+                    *reinterpret_cast<uint4*>(col + (size_t)(kc * RP + r) * 16u) = h;
+                    *reinterpret_cast<uint4*>(col + plane + (size_t)(kc * RP + r) * 16u) = l;
+                }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
