@@ -288,10 +288,12 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
         __syncwarp();
     } else if (warp == 1) {
         // ================================ loader: basis ring, two K steps per slot ================================
-        // One 12 KB bulk copy per slot; the packed basis is already in issue order.  The bulk-copy engine delivers ~27 B/clk
-        // into an SM while the MMAs could consume 43 B/clk: this stream is what the control lane waits for most (35 % of the
-        // kernel).  Tried: the second K step of each slot by 16-byte cp.async from this warp's 32 lanes (LSU path, completion
-        // through cp.async.mbarrier.arrive.noinc) - one warp's cp.async stream is latency-bound (700 cycles per slot), slower.
+        // One 12 KB bulk copy per slot; the packed basis is already in issue order.  The control lane waits for this stream
+        // more than for anything else (~40 % of the kernel: a slot arrives every ~600 cycles, the MMAs would take one every
+        // 288).  Measured and without effect: a sixth ring slot, sharing the stream with a cluster peer by multicast (half
+        // the bytes per SM), and moving the second K step of each slot to 16-byte cp.async (from this warp's 32 lanes, or
+        // from a dedicated third loader warp; completion through cp.async.mbarrier.arrive.noinc) - so it is neither ring
+        // depth nor the byte rate of the bulk-copy engine.
         if (elect_one()) {
             const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0])), ring0 = sv_opaque(smem_u32(wring));
             const uint32_t slot_bytes = 2u * kstep_bytes;
