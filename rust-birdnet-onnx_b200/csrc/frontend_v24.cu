@@ -4,24 +4,29 @@
 //   spec[b][mel][t][branch] = pow( ( sum_n  xn[b][t*hop + n] * basis[n][mel] )^2 , exponent )
 //   xn = ((x - min) / (max - min + eps) - half) * two            (per segment; min / max come from k_minmax_partial)
 //
-// What the kernel moves: the raw FP32 audio once per branch (L2-resident after the min/max pass) and the spectrogram out.
-// No normalised copy and no frame matrix ever exists in HBM:
+// What the kernel moves: the raw FP32 audio (once from HBM: the second branch reads the same range out of L2) and the
+// spectrogram out.  No normalised copy and no frame matrix ever exists in HBM.  One persistent CTA per SM, 20 warps:
 //
-//   producer warps   read the raw samples of one 128-frame tile, normalise them (same formula as the stand-alone
-//                    normaliser, division by reciprocal + residual correction), split to fp16 hi / lo and store them as a SAMPLE PATCH in shared memory:
-//                    patch row p = the `hop` samples starting at (t0 + p) * hop, kept as 16-byte cells [kcell][row].
-//                    Frame t0 + i is then rows i, i+1, ... read left to right (block-Toeplitz): the K range of block j is
-//                    the same cells shifted j rows down, which for a no-swizzle K-major UMMA operand is a start-address
-//                    shift of j * 16 bytes.  135 rows x 35 cells x 2 planes = 152 KB instead of 128 x 2240 x 2 x 2 = 1.1 MB.
-//   loader warp      streams the packed basis [k-step][W_hi | W_lo] through a ring of 1-D bulk copies (12 KB per stage).
-//   control warp     one elected lane issues, per 16-sample K step, hi * [W_hi | W_lo] (N = 2 * mels: main | correction)
-//                    and lo * W_hi (N = mels, into the correction half) into one of two TMEM accumulator sets.
+//   producer warps   read the raw samples of one 128-frame tile, normalise them (the stand-alone normaliser's formula; the
+//                    division is a reciprocal + one residual correction), split to fp16 hi / lo and store them as a
+//                    SAMPLE PATCH in shared memory: patch row p = the `hop` samples starting at (t0 + p) * hop, kept as
+//                    16-byte cells [cell][row].  Frame t0 + i is then rows i, i+1, ... read left to right (block-Toeplitz):
+//                    the K range of hop-block j is the same cells shifted j rows down, which for a no-swizzle K-major UMMA
+//                    operand is a start-address shift of j * 16 bytes.  135 rows x 35 cells x 2 planes = 152 KB instead of
+//                    128 x 2240 x 2 x 2 = 1.1 MB of frame matrix.
+//   loader lane      streams the packed basis [K step][W_hi | W_lo] through a ring of 1-D bulk copies (12 KB per slot).
+//   control lane     issues, per 16-sample K step, hi * [W_hi | W_lo] (N = 2 * mels: main | correction) and lo * W_hi
+//                    (N = mels, into the correction half) into one of two TMEM accumulator sets; table-driven, 32-bit
+//                    shared addresses formed once: it has ~144 cycles per K step.
 //   epilogue warps   TMEM -> square -> power-compress -> hi / lo planes of the [mel][frame][branch] image the stem reads,
-//                    overlapped with the MMAs of the next tile (second accumulator set).
+//                    overlapped with the MMAs of the next tile (second accumulator set).  The two branches of the same 128
+//                    frames run back to back: the first one's results wait in spare TMEM columns (tcgen05.st), the second
+//                    one's epilogue writes both channels of a pixel as one 32-bit word per plane (full sectors).
 //
-// The K loop runs cell-column pair by cell-column pair (all blocks j of a pair before the next pair), so a column pair of
+// The K loop runs cell-column pair by cell-column pair (all hop-blocks of a pair before the next pair), so a column pair of
 // the patch is dead as soon as its MMAs have completed: the producers refill it for the NEXT tile while the MMAs of this
 // tile are still running on the later columns.  The patch is its own double buffer.
+// Measurements, what bounds the kernel and what was tried: DESIGN.md section 6 (`k_spec_v24` in detail).
 #include "frontend_v24.h"
 
 #include <algorithm>
@@ -30,12 +35,6 @@
 #include <cstdlib>
 #include <cstring>
 
-#ifndef SV_SPIN_WAIT
-#define SV_SPIN_WAIT 0
-#endif
-#if SV_SPIN_WAIT
-#define BN_MBAR_TRY_WAIT 0
-#endif
 #include "tc_common.cuh"
 
 namespace bn {
@@ -45,7 +44,7 @@ namespace {
 
 constexpr int SV_EPI_WARPS = 8;                     // two per TMEM lane quarter (alternate 16-column chunks)
 constexpr int SV_PROD_WARPS = 10;
-constexpr int SV_WARPS = 2 + SV_EPI_WARPS + SV_PROD_WARPS;      // control, loader, epilogue, producers
+constexpr int SV_WARPS = 2 + SV_EPI_WARPS + SV_PROD_WARPS;      // control, loader, epilogue, producers (9 or a third loader warp: no gain)
 constexpr int SV_THREADS = SV_WARPS * 32;
 constexpr int SV_MAX_GROUPS = 24;                   // cell-column pairs of the patch
 constexpr int SV_MAX_STAGES = 12;
