@@ -49,6 +49,7 @@ constexpr int SV_THREADS = SV_WARPS * 32;
 constexpr int SV_MAX_GROUPS = 24;                   // cell-column pairs of the patch
 constexpr int SV_MAX_STAGES = 12;
 constexpr uint32_t SV_FIRST = 1u << 24, SV_LAST = 1u << 25;   // K-step table flags: first / last step of a column pair
+constexpr uint32_t SV_TRACE_SLOTS = 670;             // 3 words each: fits the 127 x 16-word scratch in front of the profile slot
 constexpr uint32_t SV_SMEM_MAX = 224 * 1024;        // + the static barriers stays under the 227 KB block limit
 
 __device__ __forceinline__ float sv_key2f(uint32_t k) {
@@ -233,6 +234,9 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
     // [3] total [4] tiles | producer warp 0: [5] wait columns free [6] total | epilogue warp 0: [7] wait MMAs [8] total |
     // loader: [9] wait ring slot [10] total
     const bool prof = PROF && p.prof != nullptr && blockIdx.x == 0;
+    // ring trace (BN_FE_DEBUG bit 1024, CTA 0): per basis slot the cycle the loader issued its copy, the cycle the control
+    // lane saw it landed and the cycle it committed the slot's MMAs -> the 127 x 16 words below the counters (tools/fe_ring_trace.py)
+    unsigned long long* trace = (prof && (p.debug & 1024)) ? p.prof - 127 * 16 : nullptr;
     unsigned long long pc0 = 0, pc1 = 0, pc2 = 0;
     const long long t_begin = PROF ? clock64() : 0;
 
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
             const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0]));
             const uint32_t gf0 = sv_opaque(smem_u32(&g_full[0])), ge0 = sv_opaque(smem_u32(&g_empty[0]));
             const uint32_t af0 = sv_opaque(smem_u32(&acc_full[0])), ae0 = sv_opaque(smem_u32(&acc_empty[0]));
-            uint32_t st = 0, wph = 0;                           // basis ring: slot, parity
+            uint32_t st = 0, wph = 0, seq = 0;                  // basis ring: slot, parity; running slot number (trace)
             SvTile t;
             for (uint32_t it = 0; sv_tile(p, (int)it, t); ++it) {
                 const uint32_t as = it & 1u;
@@ -265,6 +269,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
                 for (int s2 = 0; s2 < nslots; ++s2) {
                     const uint2 e = tab[s2];                    // the two K steps of this ring slot
                     sv_wait1<PROF>(wf0 + 8u * st, wph, pc2);
+                    if (PROF && trace && seq < SV_TRACE_SLOTS) trace[seq * 3 + 1] = (unsigned long long)(clock64() - t_begin);
                     const uint64_t db = db0 + (uint64_t)(2u * st * step16);
                     if (e.x & SV_FIRST) sv_wait1<PROF>(gf0 + ((e.x >> 13) & 0x7F8u), gpar, pc1);
                     tc_fence_after();
@@ -276,6 +281,8 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
                     umma_f16(acc + N, da_lo0 + (uint64_t)(e.y & 0xFFFFu), db + step16, idesc1, 1u);
                     if (e.y & SV_LAST) sv_commit(ge0 + ((e.y >> 13) & 0x7F8u));
                     if (CL) sv_commit_mc(we0 + 8u * st, (uint16_t)3); else sv_commit(we0 + 8u * st);
+                    if (PROF && trace && seq < SV_TRACE_SLOTS) trace[seq * 3 + 2] = (unsigned long long)(clock64() - t_begin);
+                    ++seq;
                     accum = 1u;
                     if (++st == NS) { st = 0; wph ^= 1u; }
                 }
@@ -292,7 +299,9 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
         // 288).  Measured and without effect: a sixth ring slot, sharing the stream with a cluster peer by multicast (half
         // the bytes per SM), and moving the second K step of each slot to 16-byte cp.async (from this warp's 32 lanes, or
         // from a dedicated third loader warp; completion through cp.async.mbarrier.arrive.noinc) - so it is neither ring
-        // depth nor the byte rate of the bulk-copy engine.
+        // depth nor the byte rate of the bulk-copy engine.  The ring trace (tools/fe_ring_trace.py) shows a copy landing a
+        // median 3.1 k cycles after its issue with five in flight = ~19 B/clk into the SM; giving every CTA its own copy of
+        // the basis (4 or 16 replicas) changes nothing either, so it is not contention on the shared L2 lines.
         if (elect_one()) {
             const uint32_t wf0 = sv_opaque(smem_u32(&w_full[0])), we0 = sv_opaque(smem_u32(&w_empty[0])), ring0 = sv_opaque(smem_u32(wring));
             const uint32_t slot_bytes = 2u * kstep_bytes;
@@ -304,6 +313,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_spec_v24(const SpecV24Params 
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(br.wpack);
                 for (int s2 = 0; s2 < (br.n_ksteps >> 1); ++s2, src += slot_bytes, ++seq) {
                     sv_wait1<PROF>(we0 + 8u * st, wph, pc0);
+                    if (PROF && trace && seq < SV_TRACE_SLOTS) trace[seq * 3 + 0] = (unsigned long long)(clock64() - t_begin);
                     sv_expect_tx(wf0 + 8u * st, slot_bytes);
                     if (!CL) sv_bulk_g2s(ring0 + st * slot_bytes, src, slot_bytes, wf0 + 8u * st);
                     else if ((seq & 1u) == rank) sv_bulk_g2s_mc(ring0 + st * slot_bytes, src, slot_bytes, wf0 + 8u * st, (uint16_t)3);
