@@ -82,6 +82,7 @@ extern "C" {
     pub fn bn_ctx_read_tensor(c: *mut c_void, name: *const c_char, dst: *mut f32, dst_elems: u64, elems_out: *mut u64) -> c_int;
     pub fn bn_ctx_read_normalized(c: *mut c_void, dst: *mut f32, dst_elems: u64) -> c_int;
     pub fn bn_ctx_last_launch_count(c: *const c_void) -> u64;
+    pub fn bn_ctx_last_run_in_place(c: *const c_void) -> c_int;
     pub fn bn_ctx_nonfinite_segments(c: *const c_void) -> u64;
     pub fn bn_ctx_set_profiling(c: *mut c_void, enabled: i32) -> c_int;
     pub fn bn_ctx_stage_times(c: *const c_void, ms_out: *mut f32, names_out: *mut [c_char; 48], cap: u64, n_out: *mut u64) -> c_int;
@@ -112,4 +113,6 @@ extern "C" {
     // page-locked host memory: slices that live here are DMA'd in place
     pub fn bn_host_alloc(bytes: u64) -> *mut c_void;
     pub fn bn_host_free(p: *mut c_void);
+    pub fn bn_host_register(p: *mut c_void, bytes: u64) -> c_int;
+    pub fn bn_host_unregister(p: *mut c_void) -> c_int;
 }

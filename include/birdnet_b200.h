@@ -184,6 +184,9 @@ int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems);
 /* Kernel launches enqueued by the last run on this ctx, and per-stage device times (ms) of the
  * last run when profiling was enabled with bn_ctx_set_profiling(ctx, 1). */
 uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx);
+/* 1 when the last bn_ctx_run found every segment in page-locked host memory and copied host -> device straight from the
+ * caller's slices; 0 when it gathered them into the staging slab first (batch_context.rs:199-211). */
+int bn_ctx_last_run_in_place(const bn_ctx* ctx);
 /* Segments of the last completed run on this ctx whose logits were not all finite.  The tensor-core path keeps
  * operands as fp16 hi + fp16 lo pairs: ~22 mantissa bits but the fp16 RANGE, so an activation beyond +-65504 turns
  * into NaN downstream (weights beyond it are refused at load time with BN_ERR_MODEL_LOAD).  The run still returns
@@ -248,6 +251,13 @@ int bn_device_count(void);
  * batch_context.rs:199-211) and copies host -> device straight from the caller's slices. */
 void* bn_host_alloc(uint64_t bytes);
 void bn_host_free(void* p);
+/* Page-lock memory the caller already owns (its ring buffer, a decoded recording) in place - cudaHostRegister without the
+ * caller linking the CUDA runtime.  Segments inside a registered range then take the same gather-free path; the literal
+ * pageable case is bounded by the host's pageable -> pinned memcpy rate.  Returns BN_OK or
+ * BN_ERR_INVALID_ARGUMENT (null / empty range, range already registered, registration refused by the driver).  Unregister
+ * before freeing the memory. */
+int bn_host_register(void* p, uint64_t bytes);
+int bn_host_unregister(void* p);
 
 #ifdef __cplusplus
 }

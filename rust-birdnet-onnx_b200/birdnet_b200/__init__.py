@@ -15,7 +15,7 @@ _EXPORTS = {
     "types": ("ExecutionProviderInfo", "LabelFormat", "LocationScore", "ModelConfig", "ModelType", "Prediction",
               "PredictionResult", "available_execution_providers"),
     "inference_options": ("CancellationToken", "InferenceOptions"),
-    "classifier": ("BatchInferenceContext", "Classifier", "ClassifierBuilder", "pinned_array"),
+    "classifier": ("BatchInferenceContext", "Classifier", "ClassifierBuilder", "pinned_array", "registered"),
     "rangefilter": ("RangeFilter", "RangeFilterBuilder", "calculate_week", "validate_coordinates", "validate_date"),
 }
 _WHERE = {name: mod for mod, names in _EXPORTS.items() for name in names}

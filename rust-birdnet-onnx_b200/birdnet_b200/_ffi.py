@@ -96,6 +96,7 @@ SIGNATURES = {
     "bn_ctx_read_tensor": (C.c_int, [_vp, C.c_char_p, _P(C.c_float), C.c_uint64, _P(C.c_uint64)]),
     "bn_ctx_read_normalized": (C.c_int, [_vp, _P(C.c_float), C.c_uint64]),
     "bn_ctx_last_launch_count": (C.c_uint64, [_vp]),
+    "bn_ctx_last_run_in_place": (C.c_int, [_vp]),
     "bn_ctx_nonfinite_segments": (C.c_uint64, [_vp]),
     "bn_ctx_set_profiling": (C.c_int, [_vp, C.c_int32]),
     "bn_ctx_stage_times": (C.c_int, [_vp, _P(C.c_float), _vp, C.c_uint64, _P(C.c_uint64)]),
@@ -122,6 +123,8 @@ SIGNATURES = {
     "bn_device_count": (C.c_int, []),
     "bn_host_alloc": (C.c_void_p, [C.c_uint64]),
     "bn_host_free": (None, [C.c_void_p]),
+    "bn_host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "bn_host_unregister": (C.c_int, [C.c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

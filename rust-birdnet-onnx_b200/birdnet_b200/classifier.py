@@ -188,6 +188,29 @@ def pinned_array(shape, dtype=np.float32) -> np.ndarray:
 _PINNED_OWNERS = {}
 
 
+class registered(object):
+    """Context manager: page-lock an existing numpy array in place (bn_host_register) for as long as the block runs, so
+    that segments sliced from it are copied to the GPU without the gather into the engine's staging slab.
+
+        with bb.registered(recording):                      # any C-contiguous array the caller already owns
+            results = clf.predict_batch_with_context(ctx, [recording[i] for i in range(n)])
+    """
+
+    def __init__(self, array: np.ndarray):
+        if not isinstance(array, np.ndarray) or not array.flags["C_CONTIGUOUS"] or array.nbytes == 0:
+            raise ValueError("registered(): a non-empty C-contiguous numpy array is required")
+        self._array = array
+        self._ptr = array.ctypes.data
+
+    def __enter__(self):
+        raise_for_status(_lib.bn_host_register(C.c_void_p(self._ptr), self._array.nbytes))
+        return self._array
+
+    def __exit__(self, *exc):
+        _lib.bn_host_unregister(C.c_void_p(self._ptr))
+        return False
+
+
 class BatchInferenceContext:
     """src/batch_context.rs:70-339: pinned input slab + device slabs + streams, reused."""
 
@@ -218,6 +241,10 @@ class BatchInferenceContext:
 
     def last_launch_count(self) -> int:
         return int(_lib.bn_ctx_last_launch_count(self._h))
+
+    def last_run_in_place(self) -> bool:
+        """True when the last run copied host -> device straight from the caller's page-locked slices (no gather)."""
+        return bool(_lib.bn_ctx_last_run_in_place(self._h))
 
     def nonfinite_segments(self) -> int:
         """Segments of the last run whose logits were not all finite (see bn_ctx_nonfinite_segments)."""

@@ -31,6 +31,24 @@ void* bn_host_alloc(uint64_t bytes) {
     return p;
 }
 void bn_host_free(void* p) { if (p) cudaFreeHost(p); }
+int bn_host_register(void* p, uint64_t bytes) {
+    if (!p || bytes == 0) return set_error(BN_ERR_INVALID_ARGUMENT, "bn_host_register: null pointer or empty range");
+    const cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(BN_ERR_INVALID_ARGUMENT, std::string("bn_host_register: ") + cudaGetErrorString(e));
+    }
+    return BN_OK;
+}
+int bn_host_unregister(void* p) {
+    if (!p) return set_error(BN_ERR_INVALID_ARGUMENT, "bn_host_unregister: null pointer");
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(BN_ERR_INVALID_ARGUMENT, std::string("bn_host_unregister: ") + cudaGetErrorString(e));
+    }
+    return BN_OK;
+}
 
 int bn_device_count(void) {
     int n = 0;
@@ -381,6 +399,7 @@ int bn_ctx_read_normalized(bn_ctx* ctx, float* dst, uint64_t dst_elems) {
 }
 
 uint64_t bn_ctx_last_launch_count(const bn_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+int bn_ctx_last_run_in_place(const bn_ctx* ctx) { return ctx && ctx->last_in_place ? 1 : 0; }
 uint64_t bn_ctx_nonfinite_segments(const bn_ctx* ctx) {
     return ctx && ctx->h_count ? ctx->h_count[std::max<uint64_t>(ctx->max_batch, 1)] : 0;
 }

@@ -1269,6 +1269,7 @@ int ctx_run_host(bn_ctx* c, const float* const* seg_ptrs, const uint64_t* seg_le
         th[0] = host_ms();
     }
     const bool in_place = segments_page_locked(seg_ptrs, batch, (size_t)S * sizeof(float));
+    c->last_in_place = in_place;
     if (tr) th[1] = host_ms();
     if (c->owns_stream) prof_mark(c, "h2d");
     if (!in_place || c->owns_stream) {

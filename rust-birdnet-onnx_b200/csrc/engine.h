@@ -159,6 +159,7 @@ struct bn_ctx {
     bool draining = false;
     uint64_t pending_batch = 0, pending_k = 0;
     uint64_t last_launches = 0;
+    bool last_in_place = false;   // last bn_ctx_run copied straight from the caller's page-locked slices (no gather)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<std::string> prof_names;

@@ -480,6 +480,28 @@ def test_pinned_segments_skip_the_gather_and_match(clf):
     assert np.array_equal(np.stack([r.raw_scores for r in clf.predict_batch(list(pinned[:5]))]), ref[:5])
 
 
+def test_registered_caller_memory_takes_the_in_place_path(clf):
+    """bn_host_register: memory the caller already owns, page-locked in place, is copied to the GPU without the gather
+    (the literal pageable case of batch_context.rs:199-211 pays a host memcpy per segment); results are bit-identical."""
+    B = 12
+    audio = np.ascontiguousarray(synth.batch(5, B, 144000, 48000))
+    ctx = clf.create_batch_context(B)
+    ref = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, list(audio))])
+    assert not ctx.last_run_in_place()                                     # plain numpy memory: gathered
+    with bb.registered(audio) as a:
+        got = np.stack([r.raw_scores for r in clf.predict_batch_with_context(ctx, list(a))])
+        assert ctx.last_run_in_place()
+        with pytest.raises(bb.Inference):                                   # the range is already registered
+            bb.registered(audio).__enter__()
+    assert np.array_equal(got, ref)
+    clf.predict_batch_with_context(ctx, list(audio))
+    assert not ctx.last_run_in_place()                                     # unregistered again
+    pinned = bb.pinned_array(audio.shape)
+    pinned[:] = audio
+    clf.predict_batch_with_context(ctx, list(pinned))
+    assert ctx.last_run_in_place()
+
+
 def test_predict_batch_of_any_size_runs_in_chunks(clf):
     """bn_engine_run: 300 segments = one chunk of 256 + one of 44 on a pooled internal context; the result must be
     what the batch-context path gives for the same segments (classifier.rs:676-727 takes any batch)."""
